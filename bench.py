@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- seconds per Newton step of the stationary solver on the README configuration
+(-m 300,100 -r 100 -s 1 -t 1e-10 -p 0: Q3/Q2, FGMRES + blockDiagonal), and the block SpMV's HBM
+bandwidth against the measured peak.
+
+A step = the work of one iteration of NSSolverStationary::solve_newton's inner loop
+(lab_new/src/NSSolverStationary.cpp:683-741) at the start of the run: assemble_system (Stokes
+branch, inlet imposed) -> solve_system (outer Krylov + block preconditioner with its inner solves,
+preconditioners rebuilt as the reference does) -> evaluation_point / solution update -> the
+line-search re-assembly and its residual norm.  Every step restarts from the same state
+(solution = 0, delta = 0) so that all steps do identical work.
+
+  value : step time with all inputs resident in HBM (device-side reset of the state)
+  e2e   : the same step through the C ABI with HOST buffers: the state is uploaded from pinned host
+          memory and the new solution is read back inside the timed region
+  roofline : the Jacobian block SpMV kernel, algorithmic bytes / CUDA-event time, L2 flushed
+  cpu_baseline : the CPU oracle (port of the reference path) on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "s per Newton step"
+UNIT = "s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax = float(r[1])
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def spmv_bytes(nnz_j, n):
+    # 12 B per non-zero (value + column), row pointers, x read once, y written once
+    return 12 * nnz_j + 4 * (n + 2) + 16 * n
+
+
+def parse_mesh(s):
+    a, b = s.split(",")
+    return int(a), int(b)
+
+
+def cpu_step_sample(disc, solver, prec, tol, nu, outer_cap, threads=None):
+    """Bounded sample of the step on the CPU oracle: both assemblies in full, the solve capped at
+    `outer_cap` outer iterations.  Returns (t_assemble_each, t_solve_capped, outer_done)."""
+    from oracle.pyoracle import Oracle, orc
+    if threads:
+        orc().orc_set_threads(threads)
+    o = Oracle(disc)
+    t0 = time.perf_counter()
+    o.assemble(0, True, nu)
+    t_asm = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    rc, it, fr, inner = o.solve(0, solver, prec, tol, outer_cap)
+    t_solve = time.perf_counter() - t0
+    return t_asm, t_solve, max(it, 1), int(orc().orc_get_threads())
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  deal.II / Trilinos / MPI are
+    not installable in this image, so the timed code is the oracle port of the reference path
+    (oracle/, OpenMP over the host cores).  Each step is a bounded sample: full assembly twice plus
+    the solve capped at --cpu-outer-cap outer iterations, extrapolated linearly in outer iterations
+    to the iteration count given by --cpu-outer-total (default: the cap, i.e. no extrapolation claim)."""
+    from navier_stokes_solver_b200 import binding as B
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nx, ny = parse_mesh(args.mesh)
+    d = B.Disc.generate(nx, ny)
+    nu = 1.0 / 10.0
+    times = []
+    cores = 1
+    for s in range(args.warmup + args.steps):
+        t_asm, t_solve, it, cores = cpu_step_sample(d, args.solver, args.prec, args.tol, nu, args.cpu_outer_cap)
+        total = args.cpu_outer_total or it
+        t = 2 * t_asm + t_solve * (total / it)
+        if s >= args.warmup:
+            times.append(t)
+    val = float(np.mean(times))
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": val * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"StationaryNSSolver -m {nx},{ny} -r 100 -s {args.solver} -t {args.tol:g} -p {args.prec}: first Newton step",
+                       "cells": d.ncells, "dofs": d.n},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"2 full assemblies + solve capped at {args.cpu_outer_cap} outer iterations, scaled to {args.cpu_outer_total or 'the same'} outer iterations"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="nsx", choices=["nsx", "reference"])
+    ap.add_argument("--mesh", default="300,100")
+    ap.add_argument("--solver", type=int, default=1)
+    ap.add_argument("--prec", type=int, default=0)
+    ap.add_argument("--tol", type=float, default=1e-10)
+    ap.add_argument("--ordering", type=int, default=1, help="ILU/SGS elimination order: 0 natural (as Ifpack), 1 multicolour")
+    ap.add_argument("--cpu-outer-cap", type=int, default=2)
+    ap.add_argument("--cpu-outer-total", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--kernel-reps", type=int, default=50)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from navier_stokes_solver_b200 import binding as B
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    nx, ny = parse_mesh(args.mesh)
+    nu = 1.0 / 10.0   # first Reynolds stage of the continuation (NSSolverStationary.cpp:662-665)
+    t0 = time.perf_counter()
+    d = B.Disc.generate(nx, ny)
+    dev = B.Device(d, device_id=local_rank, ordering=args.ordering)
+    setup_s = time.perf_counter() - t0
+
+    n = d.n
+    pinned_in = torch.zeros(2 * n, dtype=torch.float64).pin_memory()
+    pinned_out = torch.zeros(n, dtype=torch.float64).pin_memory()
+    stats = {}
+
+    def step(e2e):
+        if e2e:
+            dev.upload_ptr(B.VEC_SOLUTION, pinned_in.data_ptr())
+            dev.upload_ptr(B.VEC_DELTA, pinned_in.data_ptr() + 8 * n)
+        else:
+            dev.vec_set(B.VEC_SOLUTION, 0.0)
+            dev.vec_set(B.VEC_DELTA, 0.0)
+        r0 = dev.assemble(B.MODE_STOKES, True, nu)
+        rc, it, fr = dev.solve(B.STATIONARY, args.solver, args.prec, args.tol, 20000)
+        if rc != 0:
+            raise SystemExit(f"solve failed rc={rc} it={it} res={fr}")
+        dev.save_eval_point()
+        dev.update(1.0)
+        r1 = dev.assemble(B.MODE_STOKES, False, nu)
+        if e2e:
+            dev.download_ptr(B.VEC_SOLUTION, pinned_out.data_ptr())
+        stats.update(outer=it, inner_F=dev.stat("INNER_F"), inner_S=dev.stat("INNER_S"), applies=dev.stat("PRECOND_APPLIES"),
+                     r0=r0, r1=r1, final_res=fr)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        dev.synchronize()
+        torch.cuda.synchronize()
+
+    def timed(e2e, steps):
+        barrier()
+        l0 = dev.stat("KERNEL_LAUNCHES")
+        t = time.perf_counter()
+        for _ in range(steps):
+            step(e2e)
+        barrier()
+        el = time.perf_counter() - t
+        if world > 1:
+            import torch.distributed as dist
+            tt = torch.tensor([el], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            el = float(tt.item())
+        return el, dev.stat("KERNEL_LAUNCHES") - l0
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    el, launches = timed(False, args.steps)
+    el_e2e, _ = timed(True, args.steps)
+    # kernel timings (CUDA events on the library's stream, L2 flushed between launches)
+    reps = args.kernel_reps
+    rng = np.random.default_rng(42)
+    dev.upload(B.VEC_TMP0, rng.uniform(-1, 1, n))
+    dev.set_time_params(B.MODE_NEWTON, 1.0 / 90.0)
+    dev.upload(B.VEC_SOLUTION, B.synthetic_state(d, 1234))
+    for w in (0, 1, 2, 3, 4):
+        dev.time_kernel(w, 5, True)
+    k_ms = {name: dev.time_kernel(w, reps, True) for name, w in
+            (("block_spmv", 0), ("spmv_F", 1), ("assembly_newton", 2), ("dot", 3), ("axpy", 4), ("sgs_F", 5), ("ilu_apply_F", 6), ("ilu_factor_F", 7))}
+    clocks = sampler.stop()
+
+    nnz = {b: dev.nnz(b) for b in (B.BLOCK_F, B.BLOCK_BT, B.BLOCK_B, B.BLOCK_MP)}
+    nnz_j = nnz[B.BLOCK_F] + nnz[B.BLOCK_BT] + nnz[B.BLOCK_B]
+    peak, peak_kind = load_peaks()
+    bts = spmv_bytes(nnz_j, n)
+    achieved = bts / (k_ms["block_spmv"] * 1e-3) / 1e9
+    asm_bytes = 8 * (nnz_j + nnz[B.BLOCK_MP]) + 16 * n + d.ncells * (64 + 4 * 41)
+    kernels = {
+        "block_spmv": {"ms": k_ms["block_spmv"], "GBps": achieved, "frac_hbm": achieved / peak},
+        "spmv_F": {"ms": k_ms["spmv_F"], "GBps": (12 * nnz[B.BLOCK_F] + 20 * d.n_u) / (k_ms["spmv_F"] * 1e-3) / 1e9},
+        "assembly_newton": {"ms": k_ms["assembly_newton"], "GFLOPs_fp64": 1.206e5 * d.ncells / (k_ms["assembly_newton"] * 1e-3) / 1e9,
+                            "GBps_min_bytes": asm_bytes / (k_ms["assembly_newton"] * 1e-3) / 1e9},
+        "dot": {"ms": k_ms["dot"], "GBps": 16 * n / (k_ms["dot"] * 1e-3) / 1e9},
+        "axpy": {"ms": k_ms["axpy"], "GBps": 24 * n / (k_ms["axpy"] * 1e-3) / 1e9},
+        "sgs_F": {"ms": k_ms["sgs_F"], "levels": dev.stat("LEVELS_F")},
+        "ilu_apply_F": {"ms": k_ms["ilu_apply_F"]},
+        "ilu_factor_F": {"ms": k_ms["ilu_factor_F"]},
+    }
+    value = el / args.steps
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"StationaryNSSolver -m {nx},{ny} -r 100 -s {args.solver} -t {args.tol:g} -p {args.prec}: first Newton step "
+                               "(assemble + solve + update + line-search assembly)",
+                   "cells": d.ncells, "dofs": n, "nnz_J": nnz_j, "elimination_order": "multicolour" if args.ordering else "natural",
+                   "outer_iterations": stats["outer"], "inner_F_iterations": stats["inner_F"], "inner_Mp_or_S_iterations": stats["inner_S"],
+                   "final_residual": stats["final_res"], "l2_policy": "kernel timings flush L2 (256 MiB memset) between launches; step working set 0.5 GB > L2",
+                   "setup_s": setup_s},
+        "e2e": {"value": el_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n + 16},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_block_spmv (Jacobian block SpMV)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes": bts},
+        "kernels": kernels,
+    }
+    if rank == 0 and not args.no_cpu and world == 1:
+        t_asm, t_solve, it, cores = cpu_step_sample(d, args.solver, args.prec, args.tol, nu, args.cpu_outer_cap)
+        cpu_val = 2 * t_asm + t_solve * (stats["outer"] / it)
+        line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"oracle port on {cores} OpenMP threads: 2 full assemblies ({t_asm:.2f} s each) + solve capped at {it} outer "
+                                          f"iterations ({t_solve:.2f} s), scaled to the GPU run's {stats['outer']} outer iterations"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,128 @@
+/* nsx.h -- thin C ABI of the B200 (sm_100a) assembly + linear-algebra hot path.
+ *
+ * The reference (HliasGit/navier_stokes_solver) has no FFI: its hot path is reached through the
+ * C++ members NSSolverStationary::assemble_system / solve_system (lab_new/src/
+ * NSSolverStationary.cpp:317-577, 579-647) and NSSolver::assemble_system / solve_system
+ * (lab_new/src/NSSolver.cpp:313-599, 601-672), plus the vector updates of the Newton / time
+ * loops (NSSolverStationary.cpp:698, 715-729; NSSolver.cpp:707, 724-738, 820) and
+ * compute_lift_drag (NSSolverStationary.cpp:802-897).  Each entry point below names the member
+ * (file:line) whose device work it replaces.  Plain C types only: the caller owns host buffers,
+ * the library owns device memory.  One context per GPU; calls on one context are not
+ * thread-safe (as the reference objects).  Every call returns an nsx_status.
+ */
+#ifndef NSX_H
+#define NSX_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nsx_ctx nsx_ctx;
+
+enum nsx_status {
+  NSX_OK = 0,
+  NSX_E_NOCONV = 1, /* <-> deal.II SolverControl::NoConvergence (never caught by the reference) */
+  NSX_E_BADARG = 2, /* <-> std::invalid_argument (NSSolverStationary.cpp:641-643) */
+  NSX_E_CUDA = 3,
+  NSX_E_COMM = 4,
+  NSX_E_STATE = 5   /* call order violated (e.g. assemble before the pattern is set) */
+};
+
+enum nsx_block { NSX_BLOCK_F = 0, NSX_BLOCK_BT = 1, NSX_BLOCK_B = 2, NSX_BLOCK_MP = 3, NSX_BLOCK_S = 4, NSX_BLOCK_J = 5 };
+enum nsx_vec { NSX_VEC_SOLUTION = 0, NSX_VEC_SOLUTION_OLD = 1, NSX_VEC_DELTA = 2, NSX_VEC_RESIDUAL = 3, NSX_VEC_EVAL = 4,
+               NSX_VEC_TMP0 = 5, NSX_VEC_TMP1 = 6 };
+/* assembly branches: STOKES = `global_first_iter || computing_stokes` (NSSolverStationary.cpp:383-406),
+ * NEWTON (408-452), UNSTEADY_FIRST = `first_iter` (NSSolver.cpp:381-409), UNSTEADY_NEWTON (411-469) */
+enum nsx_mode { NSX_MODE_STOKES = 0, NSX_MODE_NEWTON = 1, NSX_MODE_UNSTEADY_FIRST = 2, NSX_MODE_UNSTEADY_NEWTON = 3 };
+enum nsx_flavour { NSX_STATIONARY = 0, NSX_UNSTEADY = 1 }; /* which header's preconditioner internals */
+enum nsx_option {
+  NSX_OPT_ORDERING = 0,   /* elimination order of ILU(0)/SGS: 0 natural (as Ifpack), 1 multicolour (default) */
+  NSX_OPT_VERBOSE = 1
+};
+enum nsx_stat {
+  NSX_STAT_INNER_F = 0, NSX_STAT_INNER_S = 1, NSX_STAT_PRECOND_APPLIES = 2, NSX_STAT_KERNEL_LAUNCHES = 3,
+  NSX_STAT_LEVELS_F = 4, NSX_STAT_LEVELS_MP = 5, NSX_STAT_LEVELS_S = 6, NSX_STAT_SPMV_CALLS = 7,
+  NSX_STAT_ASSEMBLY_COLOURS = 8, NSX_STAT_ASSEMBLY_TABLES = 9, NSX_STAT_LAST_STEP = 10
+};
+
+/* ctor of the solver objects (NSSolverStationary.hpp:339-351): one context per rank / GPU.
+ * stream: a cudaStream_t to run on (NULL = a stream the library creates). */
+int nsx_create(int rank, int nranks, int device_id, void *stream, nsx_ctx **out);
+int nsx_destroy(nsx_ctx *ctx);
+const char *nsx_last_error(const nsx_ctx *ctx);
+int nsx_set_option(nsx_ctx *ctx, int option, int64_t value);
+int64_t nsx_get_stat(const nsx_ctx *ctx, int stat);
+
+/* Outputs of setup() that the hot path consumes (NSSolverStationary.cpp:114-314).
+ * elem: 0 Q3/Q2 quads, 1 P2/P1 triangles.  cell_dofs: block-global ids in deal.II's cell-local
+ * FESystem order (cell->get_dof_indices, NSSolverStationary.cpp:528).  cell_vertices: per cell
+ * nvpc x (x, y). */
+int nsx_set_discretisation(nsx_ctx *ctx, int elem, int64_t n_cells, const double *cell_vertices,
+                           const uint32_t *cell_dofs, int64_t n_u, int64_t n_p);
+/* Sparsity of one block (NSSolverStationary.cpp:264-305): F, BT, B of the Jacobian and MP. */
+int nsx_set_pattern(nsx_ctx *ctx, int block, int64_t nrows, int64_t ncols, const int64_t *rowptr, const int32_t *col);
+/* Boundary faces: kind 8 = outlet Neumann term (NSSolverStationary.cpp:503-526), kind 10 = cylinder
+ * (lift/drag, NSSolverStationary.cpp:840-843). */
+int nsx_set_faces(nsx_ctx *ctx, int kind, int64_t n, const int32_t *cell, const int32_t *face);
+/* Dirichlet velocity dofs (ascending) and the inlet values of the one non-homogeneous application
+ * (interpolate_boundary_values, NSSolverStationary.cpp:541-572). */
+int nsx_set_dirichlet(nsx_ctx *ctx, int64_t n, const uint32_t *dof, const double *inlet_value);
+/* Owned ranges of the velocity / pressure blocks per rank (block_owned_dofs, NSSolverStationary.cpp:237-240):
+ * the inner ILU / SGS / AMG are local to each range (Ifpack overlap 0). */
+int nsx_set_ranks(nsx_ctx *ctx, int nranks, const int64_t *owned_u, const int64_t *owned_p);
+/* Builds the device-side gather maps; must follow the setters and precede assemble/solve. */
+int nsx_finalize_setup(nsx_ctx *ctx);
+
+/* Block vectors [velocity | pressure] of length n_u + n_p (NSSolverStationary.hpp:451-463). */
+int nsx_vec_upload(nsx_ctx *ctx, int which, const double *host);
+int nsx_vec_download(nsx_ctx *ctx, int which, double *host);
+/* device-side `v = value` and `dst = src` (Trilinos `vector = 0.0`, `a = b`; NSSolverStationary.cpp:338-340, 715) */
+int nsx_vec_set(nsx_ctx *ctx, int which, double value);
+int nsx_vec_copy(nsx_ctx *ctx, int dst, int src);
+
+/* assemble_system (NSSolverStationary.cpp:317-577, NSSolver.cpp:313-599): J, Mp, r from the current
+ * solution (and solution_old), then the Dirichlet rows; returns ||r||_2 (the l2_norm() the Newton
+ * loop takes next, NSSolverStationary.cpp:698). */
+int nsx_assemble(nsx_ctx *ctx, int mode, int apply_inlet, double nu, double dt, double p_out, double *residual_l2);
+/* solve_system (NSSolverStationary.cpp:579-647, NSSolver.cpp:601-672): solver 0 GMRES / 1 FGMRES /
+ * 2 BiCGStab; prec 0 blockDiagonal / 1 blockTriangular / 2 aSIMPLE; delta is the warm start. */
+int nsx_solve(nsx_ctx *ctx, int flavour, int solver, int prec, double tol, int max_it, double alpha,
+              int *iterations, double *final_residual);
+/* Newton / time-loop vector updates:
+ *   save_eval_point: evaluation_point = solution                    (NSSolverStationary.cpp:715)
+ *   update:          solution = evaluation_point + alpha * delta    (NSSolverStationary.cpp:720-722)
+ *   copy_old:        solution_old = solution                        (NSSolver.cpp:820) */
+int nsx_save_eval_point(nsx_ctx *ctx);
+int nsx_update(nsx_ctx *ctx, double alpha);
+int nsx_copy_old(nsx_ctx *ctx);
+/* compute_lift_drag (NSSolverStationary.cpp:802-897): forces on boundary id 10. */
+int nsx_lift_drag(nsx_ctx *ctx, double nu, double *drag_force, double *lift_force);
+
+/* ---- test / measurement hooks (no reference counterpart) ---- */
+/* the cell loop + compress of assemble_system without the Dirichlet step (structural identities) */
+int nsx_assemble_cells(nsx_ctx *ctx, int mode, double nu, double dt, double p_out);
+int nsx_get_block_nnz(nsx_ctx *ctx, int block, int64_t *nnz);
+int nsx_get_block_pattern(nsx_ctx *ctx, int block, int64_t *rowptr, int32_t *col);
+int nsx_get_block_values(nsx_ctx *ctx, int block, double *values);
+int nsx_set_block_values(nsx_ctx *ctx, int block, const double *values);
+/* y = A x on device vectors; block NSX_BLOCK_J = the whole Jacobian on block vectors */
+int nsx_spmv(nsx_ctx *ctx, int block, int vec_x, int vec_y);
+/* y = M^-1 x with one inner preconditioner on one block: kind 0 SGS, 1 ILU(0), 2 AMG */
+int nsx_inner_apply(nsx_ctx *ctx, int block, int kind, int vec_x, int vec_y);
+int nsx_ilu0_factor(nsx_ctx *ctx, int block, double *lu_values, int32_t *perm);
+int nsx_schur(nsx_ctx *ctx);
+/* dst = P^-1 src for the block preconditioner built from the current matrices */
+int nsx_precond_apply(nsx_ctx *ctx, int flavour, int prec, double alpha, int vec_src, int vec_dst);
+/* times `reps` launches of one kernel with CUDA events on the context's stream; ms per launch.
+ * what: 0 Jacobian block SpMV, 1 F SpMV, 2 assembly (matrix + rhs kernels), 3 dot, 4 axpy, 5 SGS(F) apply,
+ * 6 ILU(F) apply, 7 ILU(F) factorisation.  nsx_set_time_params picks the assembly branch that `what` = 2 times. */
+int nsx_set_time_params(nsx_ctx *ctx, int mode, double nu, double dt);
+int nsx_time_kernel(nsx_ctx *ctx, int what, int reps, int flush_l2, double *ms_per_launch);
+int nsx_synchronize(nsx_ctx *ctx);
+/* elimination order used for a block's ILU/SGS (new -> old), for oracle parity */
+int nsx_get_ordering(nsx_ctx *ctx, int block, int32_t *perm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,565 @@
+// assemble.cu -- per-cell quadrature assembly of the linearised Stokes / Newton system, its
+// right-hand side and the pressure mass matrix, straight into the device CSR blocks.
+//
+// Replaces the cell loop of NSSolverStationary::assemble_system (lab_new/src/
+// NSSolverStationary.cpp:356-533; Stokes branch 383-406, Newton branch 408-452, residual 462-493,
+// outlet term 503-526, scatter 528-532, Dirichlet step 540-576) and of NSSolver::assemble_system
+// (lab_new/src/NSSolver.cpp:358-558; first-iteration branch 381-409, Newton branch 411-469,
+// residual 479-519), plus compute_lift_drag (NSSolverStationary.cpp:835-892).
+//
+// Device layout.  Every FESystem shape function has one non-zero component, so the 41 x 41 (or
+// 15 x 15) cell matrix of the reference splits into scalar node blocks:
+//   F [(a,c),(b,c')]  velocity-velocity     Bt[(a,c),m]  velocity-pressure
+//   B [m,(b,c')]      pressure-velocity     Mp[m,m']     pressure mass
+// A group of TPC threads owns one cell: geometry, physical gradients and the fields at the
+// quadrature points are staged in shared memory next to the reference-cell tables, then the
+// threads sweep the node pairs with the quadrature sum in registers.  Cells are launched colour
+// by colour (no two cells of a colour share a dof), so the scatter `val[row_start + offset] += v`
+// needs no atomics and sums in a fixed order.  `offset` comes from a table of row-relative CSR
+// positions that cells with the same local connectivity share (a few hundred tables on the
+// structured meshes), built once with the sparsity pattern.
+#include <algorithm>
+#include <cstring>
+#include <unordered_map>
+
+#include "device.cuh"
+
+namespace nsx {
+
+// ---------------------------------------------------------------------------------------------
+// host: colouring, offset tables, outlet vector
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+inline int find_in_row(const DevCSR &A, int64_t row, int32_t col) {
+  const int32_t *b = A.h_col.data() + A.h_rowptr[row], *e = A.h_col.data() + A.h_rowptr[row + 1];
+  const int32_t *it = std::lower_bound(b, e, col);
+  if (it == e || *it != col) throw std::runtime_error("cell couples two dofs outside the sparsity pattern");
+  return (int)(it - b);
+}
+
+// reference-cell point -> Jacobian of the (bi)linear mapping, host + device
+__host__ __device__ inline void jacobian_at(int elem, const double *xv, double x, double y, double J[2][2]) {
+  if (elem == 0) {
+    const double d0x = -(1 - y), d0y = -(1 - x), d1x = (1 - y), d1y = -x, d2x = -y, d2y = (1 - x), d3x = y, d3y = x;
+    J[0][0] = xv[0] * d0x + xv[2] * d1x + xv[4] * d2x + xv[6] * d3x;
+    J[0][1] = xv[0] * d0y + xv[2] * d1y + xv[4] * d2y + xv[6] * d3y;
+    J[1][0] = xv[1] * d0x + xv[3] * d1x + xv[5] * d2x + xv[7] * d3x;
+    J[1][1] = xv[1] * d0y + xv[3] * d1y + xv[5] * d2y + xv[7] * d3y;
+  } else {
+    J[0][0] = xv[2] - xv[0]; J[0][1] = xv[4] - xv[0];
+    J[1][0] = xv[3] - xv[1]; J[1][1] = xv[5] - xv[1];
+  }
+}
+
+// outward unit normal and length of face f
+__host__ __device__ inline void face_geometry(int elem, const double *xv, int f, double &nx, double &ny, double &len) {
+  int a, b, o;
+  if (elem == 0) {
+    const int fv[4][3] = {{0, 2, 1}, {1, 3, 0}, {0, 1, 2}, {2, 3, 0}};
+    a = fv[f][0]; b = fv[f][1]; o = fv[f][2];
+  } else {
+    a = f; b = (f + 1) % 3; o = (f + 2) % 3;
+  }
+  const double tx = xv[2 * b] - xv[2 * a], ty = xv[2 * b + 1] - xv[2 * a + 1];
+  len = sqrt(tx * tx + ty * ty);
+  nx = ty / len; ny = -tx / len;
+  if (nx * (xv[2 * o] - xv[2 * a]) + ny * (xv[2 * o + 1] - xv[2 * a + 1]) > 0) { nx = -nx; ny = -ny; }
+}
+
+}  // namespace
+
+void build_assembly_maps(Ctx &c) {
+  const FETables &T = c.fe;
+  const int nd = T.ndofs, nv = T.nvpc;
+  const int64_t nc = c.ncells;
+  const uint32_t *cd = c.h_cell_dofs.data();
+
+  // --- greedy colouring over the "shares a vertex" graph; the u_x dof of a vertex names it ---
+  std::vector<int64_t> vptr(c.n_u + 1, 0);
+  for (int64_t k = 0; k < nc; ++k)
+    for (int v = 0; v < nv; ++v) vptr[cd[k * nd + 3 * v] + 1]++;
+  for (int64_t i = 0; i < c.n_u; ++i) vptr[i + 1] += vptr[i];
+  std::vector<int32_t> vcell(vptr[c.n_u]);
+  {
+    std::vector<int64_t> fill(vptr.begin(), vptr.end() - 1);
+    for (int64_t k = 0; k < nc; ++k)
+      for (int v = 0; v < nv; ++v) vcell[fill[cd[k * nd + 3 * v]]++] = (int32_t)k;
+  }
+  std::vector<int> colour(nc, -1);
+  int ncol = 0;
+  for (int64_t k = 0; k < nc; ++k) {
+    uint64_t used = 0;
+    for (int v = 0; v < nv; ++v) {
+      const uint32_t key = cd[k * nd + 3 * v];
+      for (int64_t p = vptr[key]; p < vptr[key + 1]; ++p)
+        if (colour[vcell[p]] >= 0) used |= 1ull << colour[vcell[p]];
+    }
+    int col = 0;
+    while (used & (1ull << col)) ++col;
+    if (col >= 63) throw std::runtime_error("cell colouring needs more than 63 colours");
+    colour[k] = col;
+    ncol = std::max(ncol, col + 1);
+  }
+  c.ncolors = ncol;
+  c.color_ptr.assign(ncol + 1, 0);
+  for (int64_t k = 0; k < nc; ++k) c.color_ptr[colour[k] + 1]++;
+  for (int q = 0; q < ncol; ++q) c.color_ptr[q + 1] += c.color_ptr[q];
+  std::vector<int32_t> cells(nc);
+  {
+    std::vector<int64_t> fill(c.color_ptr.begin(), c.color_ptr.end() - 1);
+    for (int64_t k = 0; k < nc; ++k) cells[fill[colour[k]]++] = (int32_t)k;
+  }
+  c.color_cells.upload(cells, c.stream);
+
+  // --- row-relative offset tables, shared between cells with the same local connectivity ---
+  const int tsz = nd * nd;
+  std::vector<uint16_t> tables;
+  std::vector<int32_t> cell_pat(nc);
+  std::unordered_map<uint64_t, std::vector<int32_t>> seen;
+  const int64_t CH = 8192;
+  std::vector<uint16_t> buf((size_t)CH * tsz);
+  std::vector<uint64_t> hash(CH);
+  std::string err;
+  for (int64_t c0 = 0; c0 < nc; c0 += CH) {
+    const int64_t c1 = std::min(nc, c0 + CH);
+#pragma omp parallel for schedule(static)
+    for (int64_t k = c0; k < c1; ++k) {
+      uint16_t *t = &buf[(size_t)(k - c0) * tsz];
+      try {
+        for (int i = 0; i < nd; ++i) {
+          const bool ip = T.dof_comp[i] == 2;
+          const int64_t ri = ip ? (int64_t)cd[k * nd + i] - c.n_u : cd[k * nd + i];
+          for (int j = 0; j < nd; ++j) {
+            const bool jp = T.dof_comp[j] == 2;
+            const int32_t cj = (int32_t)(jp ? (int64_t)cd[k * nd + j] - c.n_u : cd[k * nd + j]);
+            const DevCSR &A = ip ? (jp ? c.Mp : c.B) : (jp ? c.Bt : c.F);
+            t[i * nd + j] = (uint16_t)find_in_row(A, ri, cj);
+          }
+        }
+      } catch (const std::exception &e) {
+#pragma omp critical
+        err = e.what();
+      }
+      uint64_t h = 1469598103934665603ull;
+      for (int i = 0; i < tsz; ++i) { h ^= t[i]; h *= 1099511628211ull; }
+      hash[k - c0] = h;
+    }
+    if (!err.empty()) throw std::runtime_error(err);
+    for (int64_t k = c0; k < c1; ++k) {
+      const uint16_t *t = &buf[(size_t)(k - c0) * tsz];
+      auto &bucket = seen[hash[k - c0]];
+      int32_t id = -1;
+      for (int32_t cand : bucket)
+        if (std::memcmp(&tables[(size_t)cand * tsz], t, tsz * sizeof(uint16_t)) == 0) { id = cand; break; }
+      if (id < 0) {
+        id = (int32_t)(tables.size() / tsz);
+        tables.insert(tables.end(), t, t + tsz);
+        bucket.push_back(id);
+      }
+      cell_pat[k] = id;
+    }
+  }
+  c.npat = (int64_t)(tables.size() / tsz);
+  c.pat_off.upload(tables, c.stream);
+  c.cell_pat.upload(cell_pat, c.stream);
+
+  // --- outlet vector: -sum_faces sum_q (n . phi_i) w_f per velocity dof (NSSolverStationary.cpp:503-526) ---
+  {
+    std::map<uint32_t, double> acc;
+    for (size_t k = 0; k < c.h_outlet_cell.size(); ++k) {
+      const int64_t cell = c.h_outlet_cell[k];
+      const int f = c.h_outlet_face[k];
+      const double *xv = &c.h_cell_vertices[(size_t)cell * nv * 2];
+      double nx, ny, len;
+      face_geometry(T.elem, xv, f, nx, ny, len);
+      for (int q = 0; q < T.nqf; ++q)
+        for (int i = 0; i < nd; ++i) {
+          if (T.dof_comp[i] == 2) continue;
+          const double n_c = T.dof_comp[i] == 0 ? nx : ny;
+          acc[cd[cell * nd + i]] -= n_c * T.Nvf[f][T.dof_node[i]][q] * (T.qwf[q] * len);
+        }
+    }
+    std::vector<uint32_t> dof;
+    std::vector<double> val;
+    for (auto &kv : acc) { dof.push_back(kv.first); val.push_back(kv.second); }
+    c.n_outlet = (int64_t)dof.size();
+    c.outlet_dof.upload(dof, c.stream);
+    c.outlet_unit.upload(val, c.stream);
+  }
+  c.cyl_cell.upload(c.h_cyl_cell, c.stream);
+  c.cyl_face.upload(c.h_cyl_face, c.stream);
+  c.face_force.alloc(2 * std::max<size_t>(1, c.h_cyl_cell.size()));
+  c.d_fe.upload(&c.fe, 1, c.stream);
+  c.d_owned_u.upload(c.owned_u, c.stream);
+  c.bc_first.alloc(c.owned_u.size());
+  NSX_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// device: cell kernel
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct AsmArgs {
+  int mode;
+  double nu, inv_dt;
+  const double *sol, *sol_old;
+  double *res;
+  const int64_t *F_rp, *Bt_rp, *B_rp, *Mp_rp;
+  double *F_val, *Bt_val, *B_val, *Mp_val;
+  const double *cell_vertices;
+  const uint32_t *cell_dofs;
+  const int32_t *cell_pat;
+  const uint16_t *pat_off;
+  const int32_t *cells;
+  int ncells;
+  int64_t n_u;
+  const FETables *fe;
+};
+
+// TPC threads per cell, CPB cells per block
+template <int ELEM, int NVPC, int NVN, int NPN, int NQ, int TPC, int CPB>
+__global__ void __launch_bounds__(TPC *CPB) k_assemble(const AsmArgs A) {
+  constexpr int ND = 2 * NVN + NPN;
+  // reference-cell tables (per block)
+  __shared__ double sNv[NQ][NVN], sdNv[NQ][NVN][2], sNp[NQ][NPN], sqw[NQ], sqp[NQ][2];
+  __shared__ int sldv[NVN][2], sldp[NPN];
+  // per cell slot
+  __shared__ double sG[CPB][NQ][NVN][2], sconv[CPB][NQ][NVN], sw[CPB][NQ];
+  __shared__ double suq[CPB][NQ][2], sdu[CPB][NQ][2], sgu[CPB][NQ][4], spq[CPB][NQ];
+  __shared__ double sJi[CPB][NQ][4];
+  __shared__ double sU[CPB][NVN][2], sUo[CPB][NVN][2], sP[CPB][NPN], sxv[CPB][NVPC * 2];
+  __shared__ double se[CPB][NVN][2];
+  __shared__ int64_t srb0[CPB][ND], srb1[CPB][ND];
+  __shared__ uint32_t sdof[CPB][ND];
+
+  const int tid = threadIdx.x, slot = tid / TPC, lt = tid % TPC;
+  const FETables &T = *A.fe;
+  for (int i = tid; i < NQ * NVN; i += TPC * CPB) {
+    const int q = i / NVN, a = i % NVN;
+    sNv[q][a] = T.Nv[a][q];
+    sdNv[q][a][0] = T.dNv[a][q][0];
+    sdNv[q][a][1] = T.dNv[a][q][1];
+  }
+  for (int i = tid; i < NQ * NPN; i += TPC * CPB) sNp[i / NPN][i % NPN] = T.Np[i % NPN][i / NPN];
+  for (int i = tid; i < NQ; i += TPC * CPB) { sqw[i] = T.qw[i]; sqp[i][0] = T.qp[i][0]; sqp[i][1] = T.qp[i][1]; }
+  for (int i = tid; i < ND; i += TPC * CPB) {
+    const int comp = T.dof_comp[i], node = T.dof_node[i];
+    if (comp == 2) sldp[node] = i; else sldv[node][comp] = i;
+  }
+  __syncthreads();
+
+  const bool newton = (A.mode == NSX_MODE_NEWTON || A.mode == NSX_MODE_UNSTEADY_NEWTON);
+  const bool unsteady = (A.mode == NSX_MODE_UNSTEADY_FIRST || A.mode == NSX_MODE_UNSTEADY_NEWTON);
+  const double nu = A.nu, inv_nu = 1.0 / A.nu, inv_dt = A.inv_dt;
+  const double mass = (A.mode == NSX_MODE_UNSTEADY_NEWTON) ? inv_dt : 0.0;
+
+  for (int base = blockIdx.x * CPB; base < A.ncells; base += gridDim.x * CPB) {
+    const bool active = base + slot < A.ncells;
+    const int cell = active ? A.cells[base + slot] : 0;
+    // ---- stage 0: connectivity, coefficients, vertices ----
+    if (active) {
+      for (int i = lt; i < ND; i += TPC) {
+        const uint32_t d = A.cell_dofs[(int64_t)cell * ND + i];
+        sdof[slot][i] = d;
+        const int comp = T.dof_comp[i], node = T.dof_node[i];
+        const double s = A.sol[d];
+        if (comp == 2) {
+          sP[slot][node] = s;
+          srb0[slot][i] = A.B_rp[d - A.n_u];
+          srb1[slot][i] = A.Mp_rp[d - A.n_u];
+        } else {
+          sU[slot][node][comp] = s;
+          sUo[slot][node][comp] = unsteady ? A.sol_old[d] : 0.0;
+          srb0[slot][i] = A.F_rp[d];
+          srb1[slot][i] = A.Bt_rp[d];
+        }
+      }
+      for (int i = lt; i < NVPC * 2; i += TPC) sxv[slot][i] = A.cell_vertices[(int64_t)cell * NVPC * 2 + i];
+    }
+    __syncthreads();
+    // ---- stage 1a: geometry per quadrature point ----
+    if (active && lt < NQ) {
+      double J[2][2];
+      jacobian_at(ELEM, sxv[slot], sqp[lt][0], sqp[lt][1], J);
+      const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+      sJi[slot][lt][0] = J[1][1] / det; sJi[slot][lt][1] = -J[0][1] / det;
+      sJi[slot][lt][2] = -J[1][0] / det; sJi[slot][lt][3] = J[0][0] / det;
+      sw[slot][lt] = sqw[lt] * fabs(det);
+    }
+    __syncthreads();
+    // ---- stage 1b: physical gradients ----
+    if (active)
+      for (int i = lt; i < NQ * NVN; i += TPC) {
+        const int q = i / NVN, a = i % NVN;
+        const double g0 = sdNv[q][a][0], g1 = sdNv[q][a][1];
+        sG[slot][q][a][0] = sJi[slot][q][0] * g0 + sJi[slot][q][2] * g1;
+        sG[slot][q][a][1] = sJi[slot][q][1] * g0 + sJi[slot][q][3] * g1;
+      }
+    __syncthreads();
+    // ---- stage 1c: fields at the quadrature points ----
+    if (active && lt < NQ) {
+      const int q = lt;
+      double u0 = 0, u1 = 0, o0 = 0, o1 = 0, g00 = 0, g01 = 0, g10 = 0, g11 = 0, p = 0;
+#pragma unroll
+      for (int a = 0; a < NVN; ++a) {
+        const double n = sNv[q][a], gx = sG[slot][q][a][0], gy = sG[slot][q][a][1];
+        const double c0 = sU[slot][a][0], c1 = sU[slot][a][1];
+        u0 += c0 * n; u1 += c1 * n;
+        o0 += sUo[slot][a][0] * n; o1 += sUo[slot][a][1] * n;
+        g00 += c0 * gx; g01 += c0 * gy; g10 += c1 * gx; g11 += c1 * gy;
+      }
+#pragma unroll
+      for (int m = 0; m < NPN; ++m) p += sP[slot][m] * sNp[q][m];
+      suq[slot][q][0] = u0; suq[slot][q][1] = u1;
+      sdu[slot][q][0] = unsteady ? u0 - o0 : 0.0; sdu[slot][q][1] = unsteady ? u1 - o1 : 0.0;
+      sgu[slot][q][0] = g00; sgu[slot][q][1] = g01; sgu[slot][q][2] = g10; sgu[slot][q][3] = g11;  // [k][l] = d_l u_k
+      spq[slot][q] = p;
+    }
+    __syncthreads();
+    // ---- stage 1d: convection of each node function, first-iteration column term ----
+    if (active) {
+      for (int i = lt; i < NQ * NVN; i += TPC) {
+        const int q = i / NVN, b = i % NVN;
+        sconv[slot][q][b] = suq[slot][q][0] * sG[slot][q][b][0] + suq[slot][q][1] * sG[slot][q][b][1];
+      }
+      if (A.mode == NSX_MODE_UNSTEADY_FIRST)
+        for (int i = lt; i < NVN * 2; i += TPC) {
+          const int a = i / 2, cc = i % 2;
+          double s = 0;
+          for (int q = 0; q < NQ; ++q) s += sdu[slot][q][cc] * sNv[q][a] * inv_dt * sw[slot][q];
+          se[slot][a][cc] = s;
+        }
+    }
+    __syncthreads();
+    if (active) {
+      const uint16_t *off = A.pat_off + (int64_t)A.cell_pat[cell] * (ND * ND);
+      // ---- F: node pairs ----
+      for (int pr = lt; pr < NVN * NVN; pr += TPC) {
+        const int a = pr / NVN, b = pr % NVN;
+        double fb = 0, f00 = 0, f01 = 0, f10 = 0, f11 = 0;
+        if (newton) {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const double w = sw[slot][q];
+            const double naw = sNv[q][a] * w, nb = sNv[q][b];
+            const double v = sG[slot][q][a][0] * sG[slot][q][b][0] + sG[slot][q][a][1] * sG[slot][q][b][1];
+            const double s = naw * nb;
+            fb += nu * w * v + naw * sconv[slot][q][b] + s * mass;
+            f00 += s * sgu[slot][q][0]; f01 += s * sgu[slot][q][1];
+            f10 += s * sgu[slot][q][2]; f11 += s * sgu[slot][q][3];
+          }
+          f00 += fb; f11 += fb;
+        } else {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q)
+            fb += nu * sw[slot][q] * (sG[slot][q][a][0] * sG[slot][q][b][0] + sG[slot][q][a][1] * sG[slot][q][b][1]);
+          f00 = fb; f11 = fb;
+          if (A.mode == NSX_MODE_UNSTEADY_FIRST) {
+            f00 += se[slot][a][0]; f01 += se[slot][a][0];
+            f10 += se[slot][a][1]; f11 += se[slot][a][1];
+          }
+        }
+        const int i0 = sldv[a][0], i1 = sldv[a][1], j0 = sldv[b][0], j1 = sldv[b][1];
+        A.F_val[srb0[slot][i0] + off[i0 * ND + j0]] += f00;
+        A.F_val[srb0[slot][i1] + off[i1 * ND + j1]] += f11;
+        if (f01 != 0.0) A.F_val[srb0[slot][i0] + off[i0 * ND + j1]] += f01;
+        if (f10 != 0.0) A.F_val[srb0[slot][i1] + off[i1 * ND + j0]] += f10;
+      }
+      // ---- Bt and B: (velocity node, component) x pressure node ----
+      for (int e = lt; e < NVN * 2 * NPN; e += TPC) {
+        const int m = e % NPN, ac = e / NPN, a = ac / 2, cc = ac % 2;
+        double s = 0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) s += sG[slot][q][a][cc] * sNp[q][m] * sw[slot][q];
+        const int i = sldv[a][cc], j = sldp[m];
+        double bt = -s;
+        if (A.mode == NSX_MODE_UNSTEADY_FIRST) bt += se[slot][a][cc];
+        A.Bt_val[srb1[slot][i] + off[i * ND + j]] += bt;
+        A.B_val[srb0[slot][j] + off[j * ND + i]] += newton ? s : -s;
+      }
+      // ---- Mp ----
+      for (int e = lt; e < NPN * NPN; e += TPC) {
+        const int m = e / NPN, k = e % NPN;
+        double s = 0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) s += sNp[q][m] * sNp[q][k] * inv_nu * sw[slot][q];
+        const int i = sldp[m], j = sldp[k];
+        A.Mp_val[srb1[slot][i] + off[i * ND + j]] += s;
+      }
+      // ---- residual (Newton branches only) ----
+      if (newton)
+        for (int e = lt; e < ND; e += TPC) {
+          double r = 0;
+          if (e < NVN * 2) {
+            const int a = e / 2, cc = e % 2;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+              const double w = sw[slot][q], n = sNv[q][a];
+              const double gx = sG[slot][q][a][0], gy = sG[slot][q][a][1];
+              const double gux = sgu[slot][q][2 * cc], guy = sgu[slot][q][2 * cc + 1];
+              double t = -nu * (gux * gx + guy * gy);
+              t -= (suq[slot][q][0] * gux + suq[slot][q][1] * guy) * n;
+              t += spq[slot][q] * (cc == 0 ? gx : gy);
+              t -= sdu[slot][q][cc] * n * inv_dt;
+              r += t * w;
+            }
+            A.res[sdof[slot][sldv[a][cc]]] += r;
+          } else {
+            const int m = e - NVN * 2;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) r += (sgu[slot][q][0] + sgu[slot][q][3]) * sNp[q][m] * sw[slot][q];
+            A.res[sdof[slot][sldp[m]]] += r;
+          }
+        }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_outlet(int64_t n, const uint32_t *dof, const double *unit, double p_out, double *res) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) res[dof[i]] += p_out * unit[i];
+}
+
+// first row of each owned velocity range whose diagonal entry is non-zero
+__global__ void k_bc_first_diag(int nranks, const int64_t *owned, const int64_t *rp, const int32_t *diag, const double *val,
+                                unsigned long long *first) {
+  const int r = blockIdx.y;
+  const int64_t lo = owned[r], hi = owned[r + 1];
+  for (int64_t i = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    if ((unsigned long long)i >= first[r]) return;  // monotone: nothing earlier can come from this thread
+    if (diag[i] >= 0 && val[rp[i] + diag[i]] != 0.0) { atomicMin(&first[r], (unsigned long long)i); return; }
+  }
+}
+
+// MatrixTools::apply_boundary_values(bv, J, delta, r, false) -- NSSolverStationary.cpp:574-575
+__global__ void k_apply_bc(int64_t nbc, const uint32_t *bc_dof, const double *bc_val, int apply_inlet, int nranks, const int64_t *owned,
+                           const unsigned long long *first, const int64_t *F_rp, const int32_t *F_diag, double *F_val,
+                           const int64_t *Bt_rp, double *Bt_val, double *delta, double *res) {
+  const int G = 8;
+  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+  const int lane = threadIdx.x % G;
+  if (b >= nbc) return;
+  const int64_t i = bc_dof[b];
+  int r = 0;
+  while (r + 1 < nranks && i >= owned[r + 1]) ++r;
+  double fd = 1.0;
+  const unsigned long long fi = first[r];
+  if (fi < (unsigned long long)owned[r + 1]) fd = fabs(F_val[F_rp[fi] + F_diag[fi]]);
+  const double v = apply_inlet ? bc_val[b] : 0.0;
+  const int64_t rb = F_rp[i], re = F_rp[i + 1], dp = rb + F_diag[i];
+  double dgl = F_val[dp];
+  if (dgl == 0.0) dgl = fd;
+  __syncwarp();
+  for (int64_t k = rb + lane; k < re; k += G) F_val[k] = (k == dp) ? dgl : 0.0;
+  for (int64_t k = Bt_rp[i] + lane; k < Bt_rp[i + 1]; k += G) Bt_val[k] = 0.0;
+  if (lane == 0) { delta[i] = v; res[i] = v * dgl; }
+}
+
+// compute_lift_drag (NSSolverStationary.cpp:835-892): one thread per boundary-10 face
+__global__ void k_lift_drag(int64_t nfaces, const int32_t *fcell, const int32_t *fface, const FETables *fe, const double *cell_vertices,
+                            const uint32_t *cell_dofs, const double *sol, double nu, double *force) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= nfaces) return;
+  const FETables &T = *fe;
+  const int cell = fcell[k], f = fface[k], nd = T.ndofs;
+  const double *xv = cell_vertices + (int64_t)cell * T.nvpc * 2;
+  const uint32_t *dofs = cell_dofs + (int64_t)cell * nd;
+  double nx, ny, len;
+  face_geometry(T.elem, xv, f, nx, ny, len);
+  double drag = 0, lift = 0;
+  for (int q = 0; q < T.nqf; ++q) {
+    double x, y, J[2][2];
+    face_point(T.elem, f, T.qpf[q], x, y);
+    jacobian_at(T.elem, xv, x, y, J);
+    const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    const double Ji[2][2] = {{J[1][1] / det, -J[0][1] / det}, {-J[1][0] / det, J[0][0] / det}};
+    double g[2][2] = {{0, 0}, {0, 0}}, p = 0;
+    for (int i = 0; i < nd; ++i) {
+      const double s = sol[dofs[i]];
+      const int comp = T.dof_comp[i], node = T.dof_node[i];
+      if (comp == 2) p += s * T.Npf[f][node][q];
+      else {
+        const double g0 = T.dNvf[f][node][q][0], g1 = T.dNvf[f][node][q][1];
+        g[comp][0] += s * (Ji[0][0] * g0 + Ji[1][0] * g1);
+        g[comp][1] += s * (Ji[0][1] * g0 + Ji[1][1] * g1);
+      }
+    }
+    double st[2][2];
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) st[a][b] = (g[a][b] + g[b][a]) * nu;
+    st[0][0] -= p; st[1][1] -= p;
+    const double w = T.qwf[q] * len;
+    drag += (-st[0][0] * nx - st[0][1] * ny) * w;
+    lift += (-st[1][0] * nx - st[1][1] * ny) * w;
+  }
+  force[2 * k] = drag; force[2 * k + 1] = lift;
+}
+
+}  // namespace
+
+void assemble_cells(Ctx &c, int mode, double nu, double dt, double p_out) {
+  c.F.val.zero(c.stream); c.Bt.val.zero(c.stream); c.B.val.zero(c.stream); c.Mp.val.zero(c.stream);
+  c.vec[NSX_VEC_RESIDUAL].zero(c.stream);
+  AsmArgs A;
+  A.mode = mode; A.nu = nu; A.inv_dt = (dt != 0.0) ? 1.0 / dt : 0.0;
+  A.sol = c.vec[NSX_VEC_SOLUTION].p; A.sol_old = c.vec[NSX_VEC_SOLUTION_OLD].p; A.res = c.vec[NSX_VEC_RESIDUAL].p;
+  A.F_rp = c.F.rowptr.p; A.Bt_rp = c.Bt.rowptr.p; A.B_rp = c.B.rowptr.p; A.Mp_rp = c.Mp.rowptr.p;
+  A.F_val = c.F.val.p; A.Bt_val = c.Bt.val.p; A.B_val = c.B.val.p; A.Mp_val = c.Mp.val.p;
+  A.cell_vertices = c.cell_vertices.p; A.cell_dofs = c.cell_dofs.p; A.cell_pat = c.cell_pat.p; A.pat_off = c.pat_off.p;
+  A.n_u = c.n_u; A.fe = c.d_fe.p;
+  for (int col = 0; col < c.ncolors; ++col) {
+    const int64_t lo = c.color_ptr[col], hi = c.color_ptr[col + 1];
+    if (hi == lo) continue;
+    A.cells = c.color_cells.p + lo; A.ncells = (int)(hi - lo);
+    if (c.fe.elem == 0) {
+      constexpr int CPB = 2;
+      const int grid = (int)std::min<int64_t>((A.ncells + CPB - 1) / CPB, (int64_t)c.num_sms * 16);
+      k_assemble<0, 4, 16, 9, 16, 128, CPB><<<grid, 128 * CPB, 0, c.stream>>>(A);
+    } else {
+      constexpr int CPB = 4;
+      const int grid = (int)std::min<int64_t>((A.ncells + CPB - 1) / CPB, (int64_t)c.num_sms * 16);
+      k_assemble<1, 3, 6, 3, 7, 32, CPB><<<grid, 32 * CPB, 0, c.stream>>>(A);
+    }
+    c.stat_launches++;
+  }
+  if (c.n_outlet) {
+    k_outlet<<<(int)((c.n_outlet + 127) / 128), 128, 0, c.stream>>>(c.n_outlet, c.outlet_dof.p, c.outlet_unit.p, p_out, A.res);
+    c.stat_launches++;
+  }
+  NSX_CUDA(cudaGetLastError());
+}
+
+void apply_boundary_values(Ctx &c, bool apply_inlet) {
+  if (!c.nbc) return;
+  const int nr = (int)c.owned_u.size() - 1;
+  NSX_CUDA(cudaMemsetAsync(c.bc_first.p, 0xff, c.bc_first.n * sizeof(unsigned long long), c.stream));
+  k_bc_first_diag<<<dim3(8, nr), 256, 0, c.stream>>>(nr, c.d_owned_u.p, c.F.rowptr.p, c.F.diag.p, c.F.val.p, c.bc_first.p);
+  k_apply_bc<<<(int)((c.nbc * 8 + 255) / 256), 256, 0, c.stream>>>(c.nbc, c.bc_dof.p, c.bc_val.p, apply_inlet ? 1 : 0, nr, c.d_owned_u.p, c.bc_first.p,
+                                                                   c.F.rowptr.p, c.F.diag.p, c.F.val.p, c.Bt.rowptr.p, c.Bt.val.p,
+                                                                   c.vec[NSX_VEC_DELTA].p, c.vec[NSX_VEC_RESIDUAL].p);
+  c.stat_launches += 2;
+  NSX_CUDA(cudaGetLastError());
+}
+
+void assemble(Ctx &c, int mode, bool apply_inlet, double nu, double dt, double p_out) {
+  assemble_cells(c, mode, nu, dt, p_out);
+  apply_boundary_values(c, apply_inlet);
+}
+
+void lift_drag(Ctx &c, double nu, double *drag, double *lift) {
+  const int64_t nf = (int64_t)c.h_cyl_cell.size();
+  *drag = 0; *lift = 0;
+  if (!nf) return;
+  k_lift_drag<<<(int)((nf + 63) / 64), 64, 0, c.stream>>>(nf, c.cyl_cell.p, c.cyl_face.p, c.d_fe.p, c.cell_vertices.p, c.cell_dofs.p,
+                                                         c.vec[NSX_VEC_SOLUTION].p, nu, c.face_force.p);
+  c.stat_launches++;
+  std::vector<double> h(2 * nf);
+  NSX_CUDA(cudaMemcpyAsync(h.data(), c.face_force.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  NSX_CUDA(cudaStreamSynchronize(c.stream));
+  for (int64_t k = 0; k < nf; ++k) { *drag += h[2 * k]; *lift += h[2 * k + 1]; }  // face order, as the reference's loop
+}
+
+}  // namespace nsx

@@ -1,0 +1,228 @@
+// device.cuh -- context and shared declarations of the sm_100a library behind include/nsx.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/nsx.h"
+#include "fe.hpp"
+
+namespace nsx {
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+struct NoConvergence : std::runtime_error {
+  int last_step; double last_residual;
+  NoConvergence(int s, double r) : std::runtime_error("SolverControl::NoConvergence"), last_step(s), last_residual(r) {}
+};
+
+#define NSX_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      throw nsx::CudaError(std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void alloc(size_t count) {
+    if (count == n && p) return;
+    release();
+    if (count) NSX_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+  }
+  void upload(const T *h, size_t count, cudaStream_t s) {
+    alloc(count);
+    if (count) NSX_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T> &h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+  void zero(cudaStream_t s) { if (n) NSX_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+};
+
+// Device CSR block (pattern fixed once, values rewritten by every assembly).
+struct DevCSR {
+  int64_t nrows = 0, ncols = 0, nnz = 0;
+  int64_t row0 = 0;  // global (block-local) index of the first stored row: ranks store their owned rows only
+  DevBuf<int64_t> rowptr;
+  DevBuf<int32_t> col;
+  DevBuf<double> val;
+  DevBuf<int32_t> diag;  // offset of the diagonal inside each row (square blocks), -1 if absent
+  std::vector<int64_t> h_rowptr;  // host copies of the pattern (symbolic work is done on the host)
+  std::vector<int32_t> h_col;
+  int max_row = 0;
+};
+
+// Level-scheduled triangular machinery shared by ILU(0) and SGS on one square block.  The plan
+// holds the rank-local part of the block (couplings that cross an owned-range boundary are
+// dropped: the reference's Ifpack preconditioners run with overlap 0), permuted by the
+// elimination order (natural as Ifpack, or multicolour), rows grouped by dependency level.
+struct TriStep { int kind, l0, l1; };   // kind 0: one wide level as a grid launch; 1: levels [l0,l1) chained in one CTA
+struct TriPlan {
+  int64_t n = 0, nnz = 0;
+  int ordering = 0;
+  DevBuf<int64_t> rowptr;               // permuted, filtered pattern, columns sorted, permuted column ids
+  DevBuf<int32_t> col;
+  DevBuf<int32_t> diag;                 // offset of the diagonal inside each row
+  DevBuf<int64_t> src;                  // position in the block's value array of each entry
+  DevBuf<int32_t> perm;                 // new -> old row
+  DevBuf<int32_t> order_fwd, order_bwd; // rows sorted by forward / backward dependency level
+  DevBuf<int64_t> d_lvl_f, d_lvl_b;     // level pointers into order_*
+  DevBuf<double> val;                   // filtered values (SGS) or LU factors (ILU)
+  DevBuf<double> work, yp;              // intermediate vectors (permuted numbering)
+  bool factored = false;
+  std::vector<int64_t> h_rowptr, lvl_f, lvl_b;
+  std::vector<int32_t> h_col, h_diag, h_perm;
+  std::vector<TriStep> steps_f, steps_b;
+};
+
+struct AmgHierarchy;  // amg.cu
+
+struct Ctx {
+  int rank = 0, nranks = 1, device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  int verbose = 0;
+  int ordering = 1;
+  int num_sms = 148;
+
+  // discretisation
+  FETables fe;
+  bool have_disc = false, finalized = false;
+  int64_t ncells = 0, n_u = 0, n_p = 0, n = 0;
+  std::vector<double> h_cell_vertices;
+  std::vector<uint32_t> h_cell_dofs;
+  DevBuf<double> cell_vertices;
+  DevBuf<uint32_t> cell_dofs;
+  DevCSR F, Bt, B, Mp, S;
+  std::vector<int64_t> owned_u{0, 0}, owned_p{0, 0};
+  // Dirichlet
+  DevBuf<uint32_t> bc_dof;
+  DevBuf<double> bc_val;
+  int64_t nbc = 0;
+  // faces
+  std::vector<int32_t> h_outlet_cell, h_outlet_face, h_cyl_cell, h_cyl_face;
+  DevBuf<double> outlet_unit;     // -sum_faces sum_q (n . phi_i) w_f per outlet velocity dof (times p_out at use)
+  DevBuf<uint32_t> outlet_dof;
+  int64_t n_outlet = 0;
+  DevBuf<unsigned long long> bc_first;  // per owned range: first row with a non-zero diagonal
+  DevBuf<int32_t> cyl_cell, cyl_face;
+  // assembly: cells grouped by colour (no two cells of one colour share a dof => the scatter
+  // needs no atomics and the summation order is fixed), and per cell the id of its table of
+  // row-relative CSR offsets (identical tables are shared between cells)
+  int ncolors = 0;
+  std::vector<int64_t> color_ptr;
+  DevBuf<int32_t> color_cells;
+  DevBuf<int32_t> cell_pat;
+  DevBuf<uint16_t> pat_off;       // npat * ndofs * ndofs
+  int64_t npat = 0;
+  DevBuf<FETables> d_fe;
+  DevBuf<double> face_force;      // per cylinder face: (drag, lift)
+  DevBuf<int64_t> d_owned_u;
+  // vectors (block layout [u | p])
+  DevBuf<double> vec[7];
+  // reductions
+  DevBuf<double> red_partial;     // per-block partial sums
+  DevBuf<double> red_result;      // device scalars
+  DevBuf<unsigned int> red_counter;
+  double *h_scalars = nullptr;    // pinned
+  // preconditioner plans, keyed by block
+  std::map<int, std::unique_ptr<TriPlan>> tri;
+  std::shared_ptr<AmgHierarchy> amg;  // shared_ptr: deleter bound where the type is complete (amg.cu)
+  // aSIMPLE
+  DevBuf<double> Dvec, Dinv, delta_p, tmp_u, tmp_p;
+  bool S_symbolic = false;
+  // Krylov workspaces (outer block vectors, inner velocity / pressure vectors)
+  std::vector<DevBuf<double>> work_outer, work_inner_u, work_inner_p;
+  // statistics
+  int64_t stat_inner_F = 0, stat_inner_S = 0, stat_applies = 0, stat_launches = 0, stat_spmv = 0;
+  int last_step = 0;
+  double last_residual = 0;
+  // parameters of the assembly launch timed by nsx_time_kernel
+  int time_mode = NSX_MODE_NEWTON;
+  double time_nu = 1.0 / 90.0, time_dt = 0.01;
+  // L2 flush buffer for timing
+  DevBuf<char> flush;
+};
+
+// ---- kernels_vec.cu -------------------------------------------------------------------------
+constexpr int RED_SLOTS = 64;  // device scalar slots
+void vec_copy(Ctx &c, double *y, const double *x, int64_t n);
+void vec_set(Ctx &c, double *y, double a, int64_t n);
+void vec_scale(Ctx &c, double *y, double a, int64_t n);
+void vec_axpy(Ctx &c, double *y, double a, const double *x, int64_t n);                 // y += a x
+void vec_sadd(Ctx &c, double *y, double s, double a, const double *x, int64_t n);      // y = s y + a x
+void vec_equ(Ctx &c, double *y, double a, const double *x, int64_t n);                 // y = a x
+void vec_mul(Ctx &c, double *y, const double *d, int64_t n);                           // y *= d (element-wise)
+// y += (sign * *dev_coef) x, coefficient read on the device (no host round trip)
+void vec_axpy_dev(Ctx &c, double *y, double sign, const double *dev_coef, const double *x, int64_t n);
+// slot <- a . b (deterministic two-stage reduction; result stays on the device)
+void vec_dot_dev(Ctx &c, int slot, const double *a, const double *b, int64_t n);
+// w += (sign * *dev_coef) x ; slot <- w . v      (deal.II add_and_dot; v may alias w)
+void vec_add_and_dot_dev(Ctx &c, int slot, double *w, double sign, const double *dev_coef, const double *x, const double *v, int64_t n);
+double *slot_ptr(Ctx &c, int slot);
+// blocking reads of device scalars
+double read_slot(Ctx &c, int slot);
+void read_slots(Ctx &c, int first, int count, double *out);
+double vec_dot(Ctx &c, const double *a, const double *b, int64_t n);
+double vec_norm(Ctx &c, const double *a, int64_t n);
+double vec_add_and_dot(Ctx &c, double *w, double a, const double *x, const double *v, int64_t n);
+
+// ---- kernels_spmv.cu ------------------------------------------------------------------------
+void spmv(Ctx &c, const DevCSR &A, const double *x, double *y, bool add = false);
+void block_spmv(Ctx &c, const double *x, double *y);  // y_u = F x_u + Bt x_p ; y_p = B x_u
+void extract_diag(Ctx &c, const DevCSR &A, double *d, double *dinv);
+
+// ---- assemble.cu ----------------------------------------------------------------------------
+void build_assembly_maps(Ctx &c);
+void assemble_cells(Ctx &c, int mode, double nu, double dt, double p_out);
+void apply_boundary_values(Ctx &c, bool apply_inlet);
+void assemble(Ctx &c, int mode, bool apply_inlet, double nu, double dt, double p_out);
+void lift_drag(Ctx &c, double nu, double *drag, double *lift);
+
+// ---- trisolve.cu ----------------------------------------------------------------------------
+TriPlan &tri_plan(Ctx &c, int block);
+void tri_refresh_values(Ctx &c, TriPlan &P, const DevCSR &A);   // permuted copy of the values
+void ilu0_factor(Ctx &c, TriPlan &P, const DevCSR &A);
+void ilu0_apply(Ctx &c, TriPlan &P, double *y, const double *x);
+void sgs_apply(Ctx &c, TriPlan &P, double *y, const double *x);
+DevCSR &block_ref(Ctx &c, int block);
+
+// ---- spgemm.cu ------------------------------------------------------------------------------
+void schur_symbolic(Ctx &c);
+void schur_complement(Ctx &c);  // S = B diag(F)^-1 Bt, fills Dvec / Dinv
+
+// ---- amg.cu ---------------------------------------------------------------------------------
+void amg_setup(Ctx &c, const DevCSR &A);
+void amg_apply(Ctx &c, double *y, const double *x);
+
+// ---- krylov.cu ------------------------------------------------------------------------------
+int solve_system(Ctx &c, int flavour, int solver, int prec, double tol, int max_it, double alpha, double *final_res);
+void precond_apply_once(Ctx &c, int flavour, int prec, double alpha, const double *src, double *dst);
+
+inline int grid_for(int64_t n, int block, int max_blocks) {
+  int64_t g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+}  // namespace nsx
+
+struct nsx_ctx : nsx::Ctx {};

@@ -13,6 +13,12 @@
 #include <cmath>
 #include <cstring>
 
+#ifdef __CUDACC__
+#define NSX_HD __host__ __device__
+#else
+#define NSX_HD
+#endif
+
 namespace nsx {
 
 constexpr int MAX_DOFS = 41;  // dofs per cell (Q3/Q2)
@@ -42,6 +48,7 @@ struct FETables {
   double Nvf[MAX_FACES][MAX_VN][MAX_QF];
   double dNvf[MAX_FACES][MAX_VN][MAX_QF][2];
   double Npf[MAX_FACES][MAX_PN][MAX_QF];
+  double qpf[MAX_QF];  // face quadrature parameter t in [0,1] along the face direction
 };
 
 namespace detail {
@@ -130,7 +137,7 @@ inline void gauss01(int n, double *x, double *w) {
 }  // namespace detail
 
 // Reference face quadrature point q (parameter t in [0,1]) of face f mapped into the cell.
-inline void face_point(int elem, int f, double t, double &x, double &y) {
+NSX_HD inline void face_point(int elem, int f, double t, double &x, double &y) {
   if (elem == 0) {
     if (f == 0) { x = 0.0; y = t; }
     else if (f == 1) { x = 1.0; y = t; }
@@ -182,7 +189,7 @@ inline void build_fe_tables(int elem, FETables &T) {
         detail::feq_eval(2, eq2, m, T.qp[q][0], T.qp[q][1], T.Np[m][q], dx, dy);
       }
     }
-    for (int qf = 0; qf < 4; ++qf) T.qwf[qf] = gw[qf];
+    for (int qf = 0; qf < 4; ++qf) { T.qwf[qf] = gw[qf]; T.qpf[qf] = gx[qf]; }
     for (int f = 0; f < 4; ++f)
       for (int qf = 0; qf < 4; ++qf) {
         double x, y;
@@ -222,7 +229,7 @@ inline void build_fe_tables(int elem, FETables &T) {
     }
     double gx[3], gw[3];
     detail::gauss01(3, gx, gw);
-    for (int qf = 0; qf < 3; ++qf) T.qwf[qf] = gw[qf];
+    for (int qf = 0; qf < 3; ++qf) { T.qwf[qf] = gw[qf]; T.qpf[qf] = gx[qf]; }
     for (int f = 0; f < 3; ++f)
       for (int qf = 0; qf < 3; ++qf) {
         double x, y;

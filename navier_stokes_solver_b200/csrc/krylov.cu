@@ -1,0 +1,443 @@
+// krylov.cu -- outer and inner Krylov solvers and the three block preconditioners, device-resident.
+//
+// Replaces, for solve_system (NSSolverStationary.cpp:579-647, NSSolver.cpp:601-672):
+//   deal.II SolverGMRES / SolverFGMRES / SolverBicgstab on block vectors (K1-K3 of SURVEY.md 8a),
+//   the inner SolverFGMRES / SolverCG on single blocks (I4), and the preconditioner classes
+//   PreconditionBlockDiagonal / BlockTriangular / aSIMPLE in both flavours
+//   (NSSolverStationary.hpp:115-335, NSSolver.hpp:138-384).
+// The iteration logic (what deal.II's solvers do step by step, default AdditionalData) runs on the
+// host; every vector lives on the device and all arithmetic on vectors is a CUDA kernel.  The
+// modified Gram-Schmidt chains of GMRES / FGMRES pass their coefficients from kernel to kernel in
+// device memory (add_and_dot fused kernels), so one orthogonalisation costs one host read, not
+// one per basis vector.
+#include <cmath>
+#include <functional>
+#include <limits>
+
+#include "device.cuh"
+
+namespace nsx {
+
+namespace {
+
+typedef std::function<void(double *dst, const double *src)> DOp;
+
+enum State { ITERATE, SUCCESS, FAILURE };
+struct Control {  // deal.II SolverControl
+  int max_steps; double tol; int last_step = 0; double last_value = 0;
+  Control(int m, double t) : max_steps(m), tol(t) {}
+  State check(int step, double value) {
+    last_step = step; last_value = value;
+    if (value <= tol) return SUCCESS;
+    if (step >= max_steps || std::isnan(value)) return FAILURE;
+    return ITERATE;
+  }
+};
+
+// workspace of one solver instance: vectors of one length, allocated on first use, kept in the context
+struct Work {
+  Ctx &c;
+  std::vector<DevBuf<double>> &pool;
+  int64_t n;
+  Work(Ctx &ctx, std::vector<DevBuf<double>> &p, int64_t n_) : c(ctx), pool(p), n(n_) {}
+  double *vec(size_t i) {
+    if (pool.size() <= i) pool.resize(i + 1);
+    if (pool[i].n != (size_t)n) pool[i].alloc(n);
+    return pool[i].p;
+  }
+};
+
+// deal.II Householder::least_squares on the (m+1) x m Hessenberg matrix, H[col][row]
+double hessenberg_least_squares(const std::vector<std::vector<double>> &H, int m, double beta, std::vector<double> &y) {
+  const int rows = m + 1;
+  std::vector<double> A((size_t)rows * m), b(rows, 0.0), v(rows);
+  for (int j = 0; j < m; ++j) for (int i = 0; i < rows; ++i) A[(size_t)i * m + j] = H[j][i];
+  b[0] = beta;
+  for (int j = 0; j < m; ++j) {
+    double sigma = 0;
+    for (int i = j; i < rows; ++i) sigma += A[(size_t)i * m + j] * A[(size_t)i * m + j];
+    if (sigma == 0) continue;
+    double s = std::sqrt(sigma);
+    if (A[(size_t)j * m + j] > 0) s = -s;
+    std::fill(v.begin(), v.end(), 0.0);
+    for (int i = j; i < rows; ++i) v[i] = A[(size_t)i * m + j];
+    v[j] -= s;
+    double vv = 0;
+    for (int i = j; i < rows; ++i) vv += v[i] * v[i];
+    if (vv == 0) continue;
+    for (int cc = j; cc < m; ++cc) {
+      double t = 0;
+      for (int i = j; i < rows; ++i) t += v[i] * A[(size_t)i * m + cc];
+      t = 2 * t / vv;
+      for (int i = j; i < rows; ++i) A[(size_t)i * m + cc] -= t * v[i];
+    }
+    double t = 0;
+    for (int i = j; i < rows; ++i) t += v[i] * b[i];
+    t = 2 * t / vv;
+    for (int i = j; i < rows; ++i) b[i] -= t * v[i];
+  }
+  y.assign(m, 0.0);
+  for (int i = m - 1; i >= 0; --i) {
+    double s = b[i];
+    for (int cc = i + 1; cc < m; ++cc) s -= A[(size_t)i * m + cc] * y[cc];
+    y[i] = s / A[(size_t)i * m + i];
+  }
+  return std::fabs(b[m]);
+}
+
+// SolverCG::solve
+void solver_cg(Ctx &c, Control &ctl, const DOp &A, double *x, const double *b, const DOp &M, Work &W) {
+  const int64_t n = W.n;
+  double *g = W.vec(0), *d = W.vec(1), *h = W.vec(2);
+  int it = 0;
+  if (vec_dot(c, x, x, n) != 0.0) { A(g, x); vec_axpy(c, g, -1.0, b, n); }
+  else vec_equ(c, g, -1.0, b, n);
+  double res = vec_norm(c, g, n);
+  State conv = ctl.check(0, res);
+  if (conv != ITERATE) { if (conv != SUCCESS) throw NoConvergence(it, res); return; }
+  M(h, g);
+  vec_equ(c, d, -1.0, h, n);
+  double gh = vec_dot(c, g, h, n);
+  while (conv == ITERATE) {
+    it++;
+    A(h, d);
+    double alpha = vec_dot(c, d, h, n);
+    alpha = gh / alpha;
+    vec_axpy(c, x, alpha, d, n);
+    res = std::sqrt(std::fabs(vec_add_and_dot(c, g, alpha, h, g, n)));
+    conv = ctl.check(it, res);
+    if (conv != ITERATE) break;
+    M(h, g);
+    double beta = gh;
+    gh = vec_dot(c, g, h, n);
+    beta = gh / beta;
+    vec_sadd(c, d, beta, -1.0, h, n);
+  }
+  if (conv != SUCCESS) throw NoConvergence(it, res);
+}
+
+// SolverFGMRES::solve (max_basis_size = 30)
+void solver_fgmres(Ctx &c, Control &ctl, const DOp &A, double *x, const double *b, const DOp &M, Work &W, int slot0) {
+  const int basis_size = 30;
+  const int64_t n = W.n;
+  std::vector<std::vector<double>> H(basis_size, std::vector<double>(basis_size + 1, 0.0));
+  std::vector<double> y;
+  std::vector<char> z_used(basis_size, 0);
+  double hs[32];
+  int accumulated_iterations = 0;
+  double res = -std::numeric_limits<double>::max();
+  double *aux = W.vec(0);
+  auto v = [&](int j) { return W.vec(1 + j); };
+  auto z = [&](int j) { return W.vec(1 + basis_size + j); };
+  State state = ITERATE;
+  do {
+    A(aux, x);
+    vec_sadd(c, aux, -1.0, 1.0, b, n);
+    const double beta = vec_norm(c, aux, n);
+    res = beta;
+    state = ctl.check(accumulated_iterations, res);
+    if (state == SUCCESS) break;
+    for (auto &col : H) std::fill(col.begin(), col.end(), 0.0);
+    double a = beta;
+    y.clear();
+    for (int j = 0; j < basis_size; ++j) {
+      if (std::isfinite(a)) vec_equ(c, v(j), 1.0 / a, aux, n);
+      else vec_set(c, v(j), 0.0, n);
+      if (!z_used[j]) { vec_set(c, z(j), 0.0, n); z_used[j] = 1; }
+      M(z(j), v(j));
+      A(aux, z(j));
+      vec_dot_dev(c, slot0, aux, v(0), n);
+      for (int i = 1; i <= j; ++i) vec_add_and_dot_dev(c, slot0 + i, aux, -1.0, slot_ptr(c, slot0 + i - 1), v(i - 1), v(i), n);
+      vec_add_and_dot_dev(c, slot0 + j + 1, aux, -1.0, slot_ptr(c, slot0 + j), v(j), aux, n);
+      read_slots(c, slot0, j + 2, hs);
+      for (int i = 0; i <= j; ++i) H[j][i] = hs[i];
+      H[j][j + 1] = a = std::sqrt(hs[j + 1]);
+      if (j > 0) {
+        res = hessenberg_least_squares(H, j, beta, y);
+        state = ctl.check(++accumulated_iterations, res);
+        if (state != ITERATE) break;
+      }
+    }
+    for (size_t j = 0; j < y.size(); ++j) vec_axpy(c, x, y[j], z((int)j), n);
+  } while (state == ITERATE);
+  if (state != SUCCESS) throw NoConvergence(accumulated_iterations, res);
+}
+
+// SolverGMRES::solve (max_n_tmp_vectors = 30, left preconditioning, preconditioned residual,
+// modified Gram-Schmidt with the re-orthogonalisation test every 5th step)
+void solver_gmres(Ctx &c, Control &ctl, const DOp &A, double *x, const double *b, const DOp &M, Work &W, int slot0) {
+  const int n_tmp = 30;
+  const int64_t n = W.n;
+  std::vector<std::vector<double>> H(n_tmp - 1, std::vector<double>(n_tmp, 0.0));
+  std::vector<double> gamma(n_tmp), ci(n_tmp - 1), si(n_tmp - 1), h(n_tmp - 1);
+  std::vector<char> used(n_tmp, 0);
+  double hs[32];
+  int accumulated_iterations = 0, dim = 0;
+  State state = ITERATE;
+  double last_res = -std::numeric_limits<double>::max();
+  auto tmp = [&](int i) {
+    double *p = W.vec(i);
+    if (!used[i]) { vec_set(c, p, 0.0, n); used[i] = 1; }
+    return p;
+  };
+  double *vfirst = tmp(0);
+  double *p = tmp(n_tmp - 1);
+  bool re_orthogonalize = false;
+  do {
+    std::fill(h.begin(), h.end(), 0.0);
+    A(p, x);
+    vec_sadd(c, p, -1.0, 1.0, b, n);
+    M(vfirst, p);
+    double rho = vec_norm(c, vfirst, n);
+    last_res = rho;
+    state = ctl.check(accumulated_iterations, rho);
+    if (state != ITERATE) break;
+    gamma[0] = rho;
+    vec_scale(c, vfirst, 1.0 / rho, n);
+    for (int inner = 0; inner < n_tmp - 2 && state == ITERATE; ++inner) {
+      ++accumulated_iterations;
+      double *vv = tmp(inner + 1);
+      A(p, tmp(inner));
+      M(vv, p);
+      dim = inner + 1;
+      double norm_vv_start = 0;
+      const bool consider = (re_orthogonalize == false) && (accumulated_iterations % 5 == 0);
+      if (consider) norm_vv_start = vec_norm(c, vv, n);
+      vec_dot_dev(c, slot0, vv, tmp(0), n);
+      for (int i = 1; i < dim; ++i) vec_add_and_dot_dev(c, slot0 + i, vv, -1.0, slot_ptr(c, slot0 + i - 1), tmp(i - 1), tmp(i), n);
+      vec_add_and_dot_dev(c, slot0 + dim, vv, -1.0, slot_ptr(c, slot0 + dim - 1), tmp(dim - 1), vv, n);
+      read_slots(c, slot0, dim + 1, hs);
+      for (int i = 0; i < dim; ++i) h[i] = hs[i];
+      double norm_vv = std::sqrt(hs[dim]);
+      bool done = false;
+      if (consider) {
+        if (norm_vv > 10. * norm_vv_start * std::sqrt(std::numeric_limits<double>::epsilon())) done = true;
+        else re_orthogonalize = true;
+      }
+      if (!done && re_orthogonalize) {
+        vec_dot_dev(c, slot0, vv, tmp(0), n);
+        for (int i = 1; i < dim; ++i) vec_add_and_dot_dev(c, slot0 + i, vv, -1.0, slot_ptr(c, slot0 + i - 1), tmp(i - 1), tmp(i), n);
+        vec_add_and_dot_dev(c, slot0 + dim, vv, -1.0, slot_ptr(c, slot0 + dim - 1), tmp(dim - 1), vv, n);
+        read_slots(c, slot0, dim + 1, hs);
+        for (int i = 0; i < dim; ++i) h[i] += hs[i];
+        norm_vv = std::sqrt(hs[dim]);
+      }
+      const double s = norm_vv;
+      h[inner + 1] = s;
+      if (std::isfinite(1. / s)) vec_scale(c, vv, 1. / s, n);
+      for (int i = 0; i < inner; ++i) {
+        const double sn = si[i], cs = ci[i], dummy = h[i];
+        h[i] = cs * dummy + sn * h[i + 1];
+        h[i + 1] = -sn * dummy + cs * h[i + 1];
+      }
+      const double r = 1. / std::sqrt(h[inner] * h[inner] + h[inner + 1] * h[inner + 1]);
+      si[inner] = h[inner + 1] * r;
+      ci[inner] = h[inner] * r;
+      h[inner] = ci[inner] * h[inner] + si[inner] * h[inner + 1];
+      gamma[inner + 1] = -si[inner] * gamma[inner];
+      gamma[inner] *= ci[inner];
+      for (int i = 0; i < dim; ++i) H[inner][i] = h[i];
+      rho = std::fabs(gamma[dim]);
+      last_res = rho;
+      state = ctl.check(accumulated_iterations, rho);
+    }
+    std::vector<double> yv(dim);
+    for (int i = dim - 1; i >= 0; --i) {
+      double s = gamma[i];
+      for (int cc = i + 1; cc < dim; ++cc) s -= H[cc][i] * yv[cc];
+      yv[i] = s / H[i][i];
+    }
+    for (int i = 0; i < dim; ++i) vec_axpy(c, x, yv[i], tmp(i), n);
+  } while (state == ITERATE);
+  if (state != SUCCESS) throw NoConvergence(accumulated_iterations, last_res);
+}
+
+// SolverBicgstab::solve (exact_residual = true; breakdown threshold of deal.II >= 9.4)
+void solver_bicgstab(Ctx &c, Control &ctl, const DOp &A, double *x, const double *b, const DOp &M, Work &W) {
+  const int64_t n = W.n;
+  const double breakdown_tol = std::numeric_limits<double>::min();
+  double *r = W.vec(0), *rbar = W.vec(1), *p = W.vec(2), *y = W.vec(3), *z = W.vec(4), *t = W.vec(5), *v = W.vec(6);
+  for (double *q : {y, z, v}) vec_set(c, q, 0.0, n);
+  int step = 0;
+  double res = 0;
+  State state = ITERATE;
+  bool breakdown;
+  do {
+    breakdown = false;
+    A(r, x);
+    vec_sadd(c, r, -1.0, 1.0, b, n);
+    res = vec_norm(c, r, n);
+    {
+      const State st = ctl.check(step, res);
+      if (st == SUCCESS) { state = SUCCESS; break; }
+      if (st == FAILURE) { state = FAILURE; break; }
+    }
+    state = ITERATE;
+    double alpha = 1, omega = 1, rho = 1, rhobar, beta;
+    vec_copy(c, rbar, r, n);
+    bool startup = true;
+    do {
+      ++step;
+      rhobar = vec_dot(c, r, rbar, n);
+      if (std::fabs(rhobar) < breakdown_tol) { breakdown = true; break; }
+      beta = rhobar * alpha / (rho * omega);
+      rho = rhobar;
+      if (startup) { vec_copy(c, p, r, n); startup = false; }
+      else { vec_sadd(c, p, beta, 1.0, r, n); vec_axpy(c, p, -beta * omega, v, n); }
+      M(y, p);
+      A(v, y);
+      rhobar = vec_dot(c, rbar, v, n);
+      if (std::fabs(rhobar) < breakdown_tol) { breakdown = true; break; }
+      alpha = rho / rhobar;
+      res = std::sqrt(vec_add_and_dot(c, r, -alpha, v, r, n));
+      if (ctl.check(step, res) == SUCCESS) { vec_axpy(c, x, alpha, y, n); state = SUCCESS; break; }
+      M(z, r);
+      A(t, z);
+      rhobar = vec_dot(c, t, r, n);
+      const double t_squared = vec_dot(c, t, t, n);
+      if (t_squared < breakdown_tol) { breakdown = true; break; }
+      omega = rhobar / t_squared;
+      vec_axpy(c, x, alpha, y, n);
+      vec_axpy(c, x, omega, z, n);
+      vec_axpy(c, r, -omega, t, n);
+      A(t, x);
+      vec_axpy(c, t, -1.0, b, n);
+      res = vec_norm(c, t, n);
+      state = ctl.check(step, res);
+    } while (state == ITERATE);
+  } while (breakdown);
+  if (state != SUCCESS) throw NoConvergence(step, res);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the six preconditioner variants
+// ---------------------------------------------------------------------------------------------
+struct Preconditioner {
+  Ctx &c;
+  int flavour, type;
+  double alpha;
+  TriPlan *F = nullptr, *Mp = nullptr, *S = nullptr;
+  DOp opF, opM, opS;
+
+  Preconditioner(Ctx &ctx, int fl, int ty, double al) : c(ctx), flavour(fl), type(ty), alpha(al) {}
+
+  // the initialize() calls of solve_system: every inner preconditioner is rebuilt from the
+  // current matrix values (NSSolverStationary.cpp:583-585, 601-604, 620-626)
+  void initialize() {
+    opF = [this](double *y, const double *x) { spmv(c, c.F, x, y); };
+    opM = [this](double *y, const double *x) { spmv(c, c.Mp, x, y); };
+    opS = [this](double *y, const double *x) { spmv(c, c.S, x, y); };
+    if (type == 0) {
+      F = &tri_plan(c, NSX_BLOCK_F); Mp = &tri_plan(c, NSX_BLOCK_MP);
+      if (flavour == NSX_STATIONARY) { tri_refresh_values(c, *F, c.F); tri_refresh_values(c, *Mp, c.Mp); }
+      else { ilu0_factor(c, *F, c.F); ilu0_factor(c, *Mp, c.Mp); }
+    } else if (type == 1) {
+      Mp = &tri_plan(c, NSX_BLOCK_MP);
+      if (flavour == NSX_STATIONARY) amg_setup(c, c.F);
+      else { F = &tri_plan(c, NSX_BLOCK_F); ilu0_factor(c, *F, c.F); }
+      ilu0_factor(c, *Mp, c.Mp);
+    } else {
+      schur_complement(c);
+      F = &tri_plan(c, NSX_BLOCK_F); S = &tri_plan(c, NSX_BLOCK_S);
+      ilu0_factor(c, *F, c.F);
+      ilu0_factor(c, *S, c.S);
+      c.delta_p.alloc(c.n_p);
+      c.delta_p.zero(c.stream);
+    }
+    c.tmp_u.alloc(c.n_u);
+    c.tmp_p.alloc(c.n_p);
+  }
+
+  void vmult(double *dst, const double *src) {
+    const int64_t nu = c.n_u, np = c.n_p;
+    const double *su = src, *sp = src + nu;
+    double *du = dst, *dp = dst + nu;
+    Work WF(c, c.work_inner_u, nu), WP(c, c.work_inner_p, np);
+    const int slot_inner = 32;
+    c.stat_applies++;
+    if (flavour == NSX_STATIONARY && type == 0) {  // NSSolverStationary.hpp:132-153
+      Control cu(100001, 1e-1 * vec_norm(c, su, nu));
+      solver_fgmres(c, cu, opF, du, su, [&](double *y, const double *x) { sgs_apply(c, *F, y, x); }, WF, slot_inner);
+      c.stat_inner_F += cu.last_step;
+      Control cp(100000, 1e-1 * vec_norm(c, sp, np));
+      solver_cg(c, cp, opM, dp, sp, [&](double *y, const double *x) { sgs_apply(c, *Mp, y, x); }, WP);
+      c.stat_inner_S += cp.last_step;
+    } else if (flavour == NSX_UNSTEADY && type == 0) {  // NSSolver.hpp:155-176
+      Control cu(1000, 1e-1);
+      solver_fgmres(c, cu, opF, du, su, [&](double *y, const double *x) { ilu0_apply(c, *F, y, x); }, WF, slot_inner);
+      c.stat_inner_F += cu.last_step;
+      Control cp(1000, 1e-1);
+      solver_cg(c, cp, opM, dp, sp, [&](double *y, const double *x) { ilu0_apply(c, *Mp, y, x); }, WP);
+      c.stat_inner_S += cp.last_step;
+    } else if (type == 1) {  // NSSolverStationary.hpp:190-218, NSSolver.hpp:212-237
+      const bool st = flavour == NSX_STATIONARY;
+      Control cu(st ? 10000001 : 2000001, (st ? 1e-2 : 1e-4) * vec_norm(c, su, nu));
+      if (st) solver_fgmres(c, cu, opF, du, su, [&](double *y, const double *x) { amg_apply(c, y, x); }, WF, slot_inner);
+      else solver_fgmres(c, cu, opF, du, su, [&](double *y, const double *x) { ilu0_apply(c, *F, y, x); }, WF, slot_inner);
+      c.stat_inner_F += cu.last_step;
+      double *tmp = c.tmp_p.p;
+      spmv(c, c.B, du, tmp);
+      vec_sadd(c, tmp, -1.0, 1.0, sp, np);
+      Control cp(st ? 100000 : 2000000, (st ? 1e-2 : 1e-5) * vec_norm(c, sp, np));
+      solver_cg(c, cp, opM, dp, tmp, [&](double *y, const double *x) { ilu0_apply(c, *Mp, y, x); }, WP);
+      c.stat_inner_S += cp.last_step;
+    } else if (flavour == NSX_STATIONARY) {  // aSIMPLE, NSSolverStationary.hpp:282-311
+      Control cu(100000, 1e-1 * vec_norm(c, su, nu));
+      solver_fgmres(c, cu, opF, du, su, [&](double *y, const double *x) { ilu0_apply(c, *F, y, x); }, WF, slot_inner);
+      c.stat_inner_F += cu.last_step;
+      double *tp = c.tmp_p.p, *tu = c.tmp_u.p, *delta_p = c.delta_p.p;
+      spmv(c, c.B, du, tp);
+      vec_sadd(c, tp, -1.0, 1.0, sp, np);
+      Control cs(100000, 1e-1 * vec_norm(c, tp, np));
+      solver_cg(c, cs, opS, delta_p, tp, [&](double *y, const double *x) { ilu0_apply(c, *S, y, x); }, WP);
+      c.stat_inner_S += cs.last_step;
+      vec_scale(c, delta_p, alpha, np);
+      spmv(c, c.Bt, delta_p, tu);
+      vec_mul(c, tu, c.Dinv.p, nu);
+      vec_axpy(c, du, -1.0, tu, nu);
+      vec_copy(c, dp, delta_p, np);
+    } else {  // aSIMPLE, NSSolver.hpp:294-350
+      double *tp = c.tmp_p.p, *tu = c.tmp_u.p;
+      ilu0_apply(c, *F, du, su);
+      vec_copy(c, tp, sp, np);
+      spmv(c, c.B, du, tp, true);
+      ilu0_apply(c, *S, dp, tp);
+      vec_mul(c, du, c.Dvec.p, nu);
+      vec_scale(c, dp, 1.0 / alpha, np);
+      spmv(c, c.Bt, dp, tu);
+      vec_axpy(c, du, -1.0, tu, nu);
+      vec_mul(c, du, c.Dinv.p, nu);
+    }
+  }
+};
+
+}  // namespace
+
+int solve_system(Ctx &c, int flavour, int solver, int prec, double tol, int max_it, double alpha, double *final_res) {
+  if (prec < 0 || prec > 2)
+    throw std::invalid_argument("Invalid preconditioner type. Use 0: blockDiagonal, 1: blockTriangular, 2: aSIMPLE.");
+  c.stat_inner_F = c.stat_inner_S = c.stat_applies = 0;
+  Control ctl(max_it, tol);
+  Preconditioner pc(c, flavour, prec, alpha);
+  pc.initialize();
+  const int64_t n = c.n;
+  DOp A = [&c](double *y, const double *x) { block_spmv(c, x, y); };
+  DOp M = [&pc](double *y, const double *x) { pc.vmult(y, x); };
+  Work W(c, c.work_outer, n);
+  double *x = c.vec[NSX_VEC_DELTA].p;
+  const double *b = c.vec[NSX_VEC_RESIDUAL].p;
+  if (solver == 0) solver_gmres(c, ctl, A, x, b, M, W, 0);
+  else if (solver == 1) solver_fgmres(c, ctl, A, x, b, M, W, 0);
+  else if (solver == 2) solver_bicgstab(c, ctl, A, x, b, M, W);
+  if (final_res) *final_res = ctl.last_value;
+  return ctl.last_step;
+}
+
+void precond_apply_once(Ctx &c, int flavour, int prec, double alpha, const double *src, double *dst) {
+  if (prec < 0 || prec > 2) throw std::invalid_argument("Invalid preconditioner type.");
+  Preconditioner pc(c, flavour, prec, alpha);
+  pc.initialize();
+  pc.vmult(dst, src);
+}
+
+}  // namespace nsx

@@ -1,0 +1,107 @@
+// spgemm.cu -- approximate Schur complement S = B diag(F)^-1 Bt of the aSIMPLE preconditioner.
+//
+// Replaces PreconditionaSIMPLE::initialize (NSSolverStationary.hpp:259-275, NSSolver.hpp:275-286):
+// diag_element() loop -> D, D^-1; B.mmult(S, Bt, D^-1) (EpetraExt MatrixMatrix).  The sparsity of
+// S depends only on the patterns of B and Bt, so the symbolic product is done once on the host;
+// every call then recomputes the values on the device: one warp per row of S, the row accumulated
+// in shared memory, contributions added in the (k, l) order of the row-by-row product.
+#include <algorithm>
+
+#include "device.cuh"
+
+namespace nsx {
+
+namespace {
+
+__global__ void __launch_bounds__(256) k_schur(int64_t n_p, const int64_t *__restrict__ B_rp, const int32_t *__restrict__ B_col,
+                                               const double *__restrict__ B_val, const double *__restrict__ dinv,
+                                               const int64_t *__restrict__ Bt_rp, const int32_t *__restrict__ Bt_col,
+                                               const double *__restrict__ Bt_val, const int64_t *__restrict__ S_rp,
+                                               const int32_t *__restrict__ S_col, double *__restrict__ S_val, int maxrow) {
+  extern __shared__ double s_acc[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + wib;
+  if (row >= n_p) return;
+  double *acc = s_acc + (size_t)wib * maxrow;
+  const int64_t sb = S_rp[row];
+  const int sl = (int)(S_rp[row + 1] - sb);
+  for (int t = lane; t < sl; t += 32) acc[t] = 0.0;
+  __syncwarp();
+  for (int64_t k = B_rp[row]; k < B_rp[row + 1]; ++k) {
+    const int32_t m = B_col[k];
+    const double a = B_val[k] * dinv[m];
+    for (int64_t l = Bt_rp[m] + lane; l < Bt_rp[m + 1]; l += 32) {
+      const int32_t cj = Bt_col[l];
+      int lo = 0, hi = sl;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (S_col[sb + mid] < cj) lo = mid + 1; else hi = mid;
+      }
+      acc[lo] += a * Bt_val[l];
+    }
+    __syncwarp();
+  }
+  for (int t = lane; t < sl; t += 32) S_val[sb + t] = acc[t];
+}
+
+}  // namespace
+
+void schur_symbolic(Ctx &c) {
+  if (c.S_symbolic) return;
+  const DevCSR &B = c.B, &Bt = c.Bt;
+  DevCSR &S = c.S;
+  const int64_t n = c.n_p;
+  S.nrows = S.ncols = n;
+  std::vector<std::vector<int32_t>> rows(n);
+#pragma omp parallel
+  {
+    std::vector<int32_t> tmp;
+#pragma omp for schedule(dynamic, 256)
+    for (int64_t i = 0; i < n; ++i) {
+      tmp.clear();
+      for (int64_t k = B.h_rowptr[i]; k < B.h_rowptr[i + 1]; ++k) {
+        const int64_t m = B.h_col[k];
+        tmp.insert(tmp.end(), Bt.h_col.begin() + Bt.h_rowptr[m], Bt.h_col.begin() + Bt.h_rowptr[m + 1]);
+      }
+      std::sort(tmp.begin(), tmp.end());
+      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+      rows[i] = tmp;
+    }
+  }
+  S.h_rowptr.assign(n + 1, 0);
+  for (int64_t i = 0; i < n; ++i) S.h_rowptr[i + 1] = S.h_rowptr[i] + (int64_t)rows[i].size();
+  S.nnz = S.h_rowptr[n];
+  S.h_col.resize(S.nnz);
+  std::vector<int32_t> diag(n, -1);
+  S.max_row = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    std::copy(rows[i].begin(), rows[i].end(), S.h_col.begin() + S.h_rowptr[i]);
+    S.max_row = std::max<int>(S.max_row, (int)rows[i].size());
+    auto it = std::lower_bound(rows[i].begin(), rows[i].end(), (int32_t)i);
+    if (it != rows[i].end() && *it == i) diag[i] = (int32_t)(it - rows[i].begin());
+  }
+  S.rowptr.upload(S.h_rowptr, c.stream);
+  S.col.upload(S.h_col, c.stream);
+  S.diag.upload(diag, c.stream);
+  S.val.alloc(S.nnz);
+  S.val.zero(c.stream);
+  c.Dvec.alloc(c.n_u);
+  c.Dinv.alloc(c.n_u);
+  NSX_CUDA(cudaStreamSynchronize(c.stream));
+  c.tri.erase(NSX_BLOCK_S);
+  c.S_symbolic = true;
+}
+
+void schur_complement(Ctx &c) {
+  schur_symbolic(c);
+  extract_diag(c, c.F, c.Dvec.p, c.Dinv.p);
+  const int wpb = 8;
+  const size_t smem = (size_t)wpb * c.S.max_row * sizeof(double);
+  if (smem > 48 * 1024) throw std::runtime_error("Schur complement row too long for the shared-memory accumulator");
+  k_schur<<<(int)((c.n_p + wpb - 1) / wpb), wpb * 32, smem, c.stream>>>(c.n_p, c.B.rowptr.p, c.B.col.p, c.B.val.p, c.Dinv.p, c.Bt.rowptr.p,
+                                                                       c.Bt.col.p, c.Bt.val.p, c.S.rowptr.p, c.S.col.p, c.S.val.p, c.S.max_row);
+  c.stat_launches++;
+  NSX_CUDA(cudaGetLastError());
+}
+
+}  // namespace nsx

@@ -1,0 +1,108 @@
+"""GPU sparse / vector / inner-preconditioner kernels against the CPU oracle (through the C ABI)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import nsxlib as N
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=["quad", "tri"])
+def setup(request):
+    d = N.Disc.generate(16, 8) if request.param == "quad" else N.Disc.generate(12, 6, triangles=True)
+    orc, dev = N.Oracle(d), N.Device(d, ordering=0)
+    sol = N.synthetic_state(d, 21)
+    orc.vec(0)[:] = sol
+    dev.upload(N.VEC_SOLUTION, sol)
+    orc.assemble(N.MODE_NEWTON, False, 1 / 50.0)
+    dev.assemble(N.MODE_NEWTON, False, 1 / 50.0)
+    # identical matrices on both sides from here on
+    for blk in (N.BLOCK_F, N.BLOCK_BT, N.BLOCK_B, N.BLOCK_MP):
+        dev.set_values(blk, orc.values(blk))
+    return d, orc, dev
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def test_spmv_blocks(setup):
+    d, orc, dev = setup
+    rng = np.random.default_rng(42)
+    x = rng.uniform(-1, 1, d.n)
+    assert rel(dev.spmv(N.BLOCK_J, x), orc.spmv(N.BLOCK_J, x)) < 1e-13
+    for blk, ncols in ((N.BLOCK_F, d.n_u), (N.BLOCK_BT, d.n_p), (N.BLOCK_B, d.n_u), (N.BLOCK_MP, d.n_p)):
+        xb = rng.uniform(-1, 1, ncols)
+        assert rel(dev.spmv(blk, xb), orc.spmv(blk, xb)) < 1e-13
+
+
+@pytest.mark.parametrize("block", [N.BLOCK_F, N.BLOCK_MP])
+def test_sgs_natural_matches_oracle(setup, block):
+    d, orc, dev = setup
+    n = d.n_u if block == N.BLOCK_F else d.n_p
+    x = np.random.default_rng(1).uniform(-1, 1, n)
+    assert rel(dev.inner_apply(block, 0, x), orc.inner_apply(block, 0, x)) < 1e-11
+
+
+@pytest.mark.parametrize("block", [N.BLOCK_F, N.BLOCK_MP])
+def test_ilu0_natural_matches_oracle(setup, block):
+    d, orc, dev = setup
+    n = d.n_u if block == N.BLOCK_F else d.n_p
+    lu_d, perm = dev.ilu0_factor(block)
+    np.testing.assert_array_equal(perm, np.arange(n))
+    lu_o = orc.ilu0_factor(block)
+    assert rel(lu_d, lu_o) < 1e-11
+    x = np.random.default_rng(2).uniform(-1, 1, n)
+    assert rel(dev.inner_apply(block, 1, x), orc.inner_apply(block, 1, x)) < 1e-10
+
+
+def test_schur_complement(setup):
+    d, orc, dev = setup
+    S_o = orc.schur()
+    S_d = dev.schur()
+    assert (S_o.indptr == S_d.indptr).all() and (S_o.indices == S_d.indices).all()
+    assert rel(S_d.data, S_o.data) < 1e-12
+    # and against scipy's product
+    F = orc.csr(N.BLOCK_F)
+    ref = (orc.csr(N.BLOCK_B) @ sp.diags(1.0 / F.diagonal()) @ orc.csr(N.BLOCK_BT)).toarray()
+    assert np.abs(S_d.toarray() - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("ordering", [0, 1])
+@pytest.mark.parametrize("block,kind", [(N.BLOCK_F, 0), (N.BLOCK_F, 1), (N.BLOCK_MP, 0), (N.BLOCK_MP, 1)])
+def test_inner_preconditioners_by_definition(setup, ordering, block, kind):
+    """Both elimination orders against a dense restatement of the definition on the permuted matrix:
+    SGS = (D+U)^-1 D (D+L)^-1, ILU(0) = the incomplete factors restricted to the pattern."""
+    d, orc, dev = setup
+    dev.set_option(N.OPT_ORDERING, ordering)
+    try:
+        A = orc.csr(block).toarray()
+        n = A.shape[0]
+        perm = dev.ordering(block)
+        assert sorted(perm.tolist()) == list(range(n))
+        Ap = A[np.ix_(perm, perm)]
+        x = np.random.default_rng(3).uniform(-1, 1, n)
+        y = dev.inner_apply(block, kind, x)
+        if kind == 0:
+            D = np.diag(np.diag(Ap))
+            Lo, Up = np.tril(Ap, -1), np.triu(Ap, 1)
+            w = np.linalg.solve(D + Lo, x[perm])
+            yp = np.linalg.solve(D + Up, D @ w)
+        else:
+            pat = Ap != 0
+            LU = Ap.copy()
+            for i in range(n):
+                for k in np.nonzero(pat[i, :i])[0]:
+                    LU[i, k] /= LU[k, k]
+                    js = np.nonzero(pat[i, k + 1:] & pat[k, k + 1:])[0] + k + 1
+                    LU[i, js] -= LU[i, k] * LU[k, js]
+            Lm = np.tril(LU, -1) + np.eye(n)
+            yp = np.linalg.solve(np.triu(LU), np.linalg.solve(Lm, x[perm]))
+        ref = np.empty(n)
+        ref[perm] = yp
+        assert rel(y, ref) < 1e-9
+        if ordering == 1:
+            assert dev.stat("LEVELS_F" if block == N.BLOCK_F else "LEVELS_MP") < 200
+    finally:
+        dev.set_option(N.OPT_ORDERING, 0)

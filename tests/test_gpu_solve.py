@@ -1,0 +1,94 @@
+"""solve_system on the GPU (nsx_solve) against the CPU oracle: same matrices, same right-hand side,
+same warm start, natural elimination order (as Ifpack) so that the two runs do the same arithmetic
+up to summation order.  Tolerances: converged increment to 1e-8 relative L2 (north_star); iteration
+counts are asserted equal on these small cases and reported side by side at scale (bench.py)."""
+import numpy as np
+import pytest
+
+import nsxlib as N
+
+pytestmark = pytest.mark.gpu
+
+
+def make(elem, mode, nu, nranks=1):
+    d = N.Disc.generate(20, 8, nranks=nranks) if elem == "quad" else N.Disc.generate(16, 7, triangles=True, nranks=nranks)
+    orc, dev = N.Oracle(d), N.Device(d, ordering=0)
+    sol = N.synthetic_state(d, 99, noise=1e-4)
+    for o in (orc,):
+        o.vec(0)[:] = sol
+        o.vec(1)[:] = sol
+        o.vec(2)[:] = 0
+    dev.upload(N.VEC_SOLUTION, sol)
+    dev.upload(N.VEC_SOLUTION_OLD, sol)
+    dev.upload(N.VEC_DELTA, np.zeros(d.n))
+    orc.assemble(mode, True, nu, 0.01)
+    dev.assemble(mode, True, nu, 0.01)
+    for blk in (N.BLOCK_F, N.BLOCK_BT, N.BLOCK_B, N.BLOCK_MP):
+        dev.set_values(blk, orc.values(blk))
+    dev.upload(N.VEC_RESIDUAL, orc.vec(3))
+    dev.upload(N.VEC_DELTA, orc.vec(2))
+    return d, orc, dev
+
+
+CASES = [
+    # flavour, solver, prec, mode, elem
+    (N.STATIONARY, 1, 0, N.MODE_STOKES, "quad"),     # README config: FGMRES + blockDiagonal
+    (N.STATIONARY, 1, 0, N.MODE_NEWTON, "quad"),
+    (N.STATIONARY, 0, 0, N.MODE_NEWTON, "tri"),      # GMRES
+    (N.STATIONARY, 1, 2, N.MODE_NEWTON, "quad"),     # aSIMPLE, stationary flavour
+    (N.STATIONARY, 1, 2, N.MODE_STOKES, "tri"),
+    (N.UNSTEADY, 1, 0, N.MODE_UNSTEADY_NEWTON, "tri"),
+    (N.UNSTEADY, 1, 1, N.MODE_UNSTEADY_NEWTON, "tri"),
+    (N.UNSTEADY, 1, 2, N.MODE_UNSTEADY_NEWTON, "tri"),   # config 3: FGMRES + aSIMPLE, unsteady flavour
+    (N.UNSTEADY, 0, 2, N.MODE_UNSTEADY_NEWTON, "quad"),
+    (N.UNSTEADY, 2, 2, N.MODE_UNSTEADY_FIRST, "quad"),
+]
+
+
+@pytest.mark.parametrize("flavour,solver,prec,mode,elem", CASES)
+def test_solve_matches_oracle(flavour, solver, prec, mode, elem):
+    d, orc, dev = make(elem, mode, 1 / 10.0)
+    tol = 1e-12
+    rc_o, it_o, fr_o, inner = orc.solve(flavour, solver, prec, tol, 2000)
+    rc_d, it_d, fr_d = dev.solve(flavour, solver, prec, tol, 2000)
+    print(f"oracle: rc {rc_o} it {it_o} res {fr_o:.3e} inner {inner.tolist()} | gpu: rc {rc_d} it {it_d} res {fr_d:.3e} "
+          f"inner [{dev.stat('INNER_F')}, {dev.stat('INNER_S')}, {dev.stat('PRECOND_APPLIES')}]")
+    assert rc_o == 0 and rc_d == 0
+    x_o, x_d = orc.vec(2), dev.download(N.VEC_DELTA)
+    assert np.linalg.norm(x_d - x_o) <= 1e-8 * np.linalg.norm(x_o)
+    assert abs(it_d - it_o) <= max(3, 0.1 * it_o)   # rounding flips inner stopping tests now and then
+    # and the answer solves the system: || J x - r || <= tol-ish
+    J = orc.jacobian()
+    assert np.linalg.norm(J @ x_d - orc.vec(3)) <= 50 * tol
+
+
+def test_two_rank_local_preconditioners():
+    """Owned ranges of a 2-rank partition: ILU / SGS drop the couplings across the range boundary
+    (Ifpack overlap 0) on both sides alike."""
+    d, orc, dev = make("tri", N.MODE_NEWTON, 1 / 10.0, nranks=2)
+    assert d.nranks == 2
+    rc_o, it_o, fr_o, _ = orc.solve(N.STATIONARY, 1, 2, 1e-12, 2000)
+    rc_d, it_d, fr_d = dev.solve(N.STATIONARY, 1, 2, 1e-12, 2000)
+    assert rc_o == 0 and rc_d == 0 and abs(it_o - it_d) <= max(3, 0.1 * it_o)
+    assert np.linalg.norm(dev.download(N.VEC_DELTA) - orc.vec(2)) <= 1e-8 * np.linalg.norm(orc.vec(2))
+
+
+def test_error_codes():
+    d, orc, dev = make("tri", N.MODE_NEWTON, 1 / 10.0)
+    rc, _, _ = dev.solve(N.STATIONARY, 1, 7, 1e-10, 100)   # std::invalid_argument in the reference
+    assert rc == N.NSX_E_BADARG
+    rc, it, res = dev.solve(N.STATIONARY, 1, 2, 1e-30, 3)   # SolverControl::NoConvergence
+    assert rc == N.NSX_E_NOCONV and it == 3 and res > 0
+    # solver outside {0,1,2}: the reference solves nothing and returns last_step() = 0
+    rc, it, _ = dev.solve(N.STATIONARY, 5, 2, 1e-10, 100)
+    assert rc == N.NSX_OK and it == 0
+
+
+def test_multicolour_order_converges_to_the_same_answer():
+    d, orc, dev = make("quad", N.MODE_NEWTON, 1 / 10.0)
+    rc_o, it_o, _, _ = orc.solve(N.STATIONARY, 1, 0, 1e-12, 2000)
+    dev.set_option(N.OPT_ORDERING, 1)
+    rc_d, it_d, _ = dev.solve(N.STATIONARY, 1, 0, 1e-12, 2000)
+    print("natural (oracle)", it_o, "multicolour (gpu)", it_d)
+    assert rc_d == 0
+    assert np.linalg.norm(dev.download(N.VEC_DELTA) - orc.vec(2)) <= 1e-7 * np.linalg.norm(orc.vec(2))
