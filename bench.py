@@ -147,7 +147,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="nsx", choices=["nsx", "reference"])
     ap.add_argument("--mesh", default="300,100")
@@ -155,7 +155,7 @@ def main():
     ap.add_argument("--prec", type=int, default=0)
     ap.add_argument("--tol", type=float, default=1e-10)
     ap.add_argument("--ordering", type=int, default=1, help="ILU/SGS elimination order: 0 natural (as Ifpack), 1 multicolour")
-    ap.add_argument("--cpu-outer-cap", type=int, default=2)
+    ap.add_argument("--cpu-outer-cap", type=int, default=1)
     ap.add_argument("--cpu-outer-total", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--kernel-reps", type=int, default=50)

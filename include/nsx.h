@@ -37,7 +37,10 @@ enum nsx_mode { NSX_MODE_STOKES = 0, NSX_MODE_NEWTON = 1, NSX_MODE_UNSTEADY_FIRS
 enum nsx_flavour { NSX_STATIONARY = 0, NSX_UNSTEADY = 1 }; /* which header's preconditioner internals */
 enum nsx_option {
   NSX_OPT_ORDERING = 0,   /* elimination order of ILU(0)/SGS: 0 natural (as Ifpack), 1 multicolour (default) */
-  NSX_OPT_VERBOSE = 1
+  NSX_OPT_VERBOSE = 1,
+  NSX_OPT_ORTHO = 2,      /* Gram-Schmidt of GMRES/FGMRES: 0 modified chain (as deal.II), 1 batched classical, two passes (default) */
+  NSX_OPT_COOP_SWEEP = 3, /* multicolour sweeps as one cooperative launch (default 1) */
+  NSX_OPT_STREAM_SPMV = 4 /* SpMV kernel: 2 TMA-fed persistent (default), 1 streaming with plain loads, 0 sub-warp per row */
 };
 enum nsx_stat {
   NSX_STAT_INNER_F = 0, NSX_STAT_INNER_S = 1, NSX_STAT_PRECOND_APPLIES = 2, NSX_STAT_KERNEL_LAUNCHES = 3,

@@ -25,7 +25,7 @@ MODE_STOKES, MODE_NEWTON, MODE_UNSTEADY_FIRST, MODE_UNSTEADY_NEWTON = 0, 1, 2, 3
 VEC_SOLUTION, VEC_SOLUTION_OLD, VEC_DELTA, VEC_RESIDUAL, VEC_EVAL, VEC_TMP0, VEC_TMP1 = 0, 1, 2, 3, 4, 5, 6
 STATIONARY, UNSTEADY = 0, 1
 NSX_OK, NSX_E_NOCONV, NSX_E_BADARG, NSX_E_CUDA, NSX_E_COMM, NSX_E_STATE = 0, 1, 2, 3, 4, 5
-OPT_ORDERING, OPT_VERBOSE = 0, 1
+OPT_ORDERING, OPT_VERBOSE, OPT_ORTHO, OPT_COOP_SWEEP, OPT_STREAM_SPMV = 0, 1, 2, 3, 4
 STAT = dict(INNER_F=0, INNER_S=1, PRECOND_APPLIES=2, KERNEL_LAUNCHES=3, LEVELS_F=4, LEVELS_MP=5, LEVELS_S=6,
             SPMV_CALLS=7, ASSEMBLY_COLOURS=8, ASSEMBLY_TABLES=9, LAST_STEP=10)
 # every entry point include/nsx.h declares (tests check that the library exports each one)
@@ -181,7 +181,7 @@ class Device:
     """One GPU context of the hot path (include/nsx.h) filled from a Disc.  Every method is a thin call
     through the C ABI; there is no CPU fallback (construction fails without a CUDA device)."""
 
-    def __init__(self, disc, device_id=0, inlet_amplitude=0.1, ordering=None, stream=None):
+    def __init__(self, disc, device_id=0, inlet_amplitude=0.1, ordering=None, stream=None, ortho=None):
         L = nsx()
         self.disc = disc
         self.n_u, self.n_p, self.n = disc.n_u, disc.n_p, disc.n
@@ -192,6 +192,8 @@ class Device:
         self.h = h
         if ordering is not None:
             self._ck(L.nsx_set_option(self.h, OPT_ORDERING, ordering))
+        if ortho is not None:
+            self._ck(L.nsx_set_option(self.h, OPT_ORTHO, ortho))
         cd = np.ascontiguousarray(disc.array("CELL_DOFS"))
         cv = np.ascontiguousarray(disc.array("CELL_VERTICES"))
         self._ck(L.nsx_set_discretisation(self.h, disc.elem, disc.ncells, ptr(cv), ptr(cd), disc.n_u, disc.n_p))

@@ -30,10 +30,13 @@ void set_block(Ctx &c, DevCSR &A, int64_t nrows, int64_t ncols, const int64_t *r
   A.h_rowptr.assign(rowptr, rowptr + nrows + 1);
   A.nnz = rowptr[nrows];
   A.h_col.assign(col, col + A.nnz);
-  A.rowptr.upload(A.h_rowptr, c.stream);
-  A.col.upload(A.h_col, c.stream);
-  A.val.alloc(A.nnz);
-  A.val.zero(c.stream);
+  A.rowptr.alloc_padded(A.h_rowptr.size(), 4);
+  NSX_CUDA(cudaMemcpyAsync(A.rowptr.p, A.h_rowptr.data(), A.h_rowptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
+  A.col.alloc_padded(A.nnz, 8);
+  NSX_CUDA(cudaMemcpyAsync(A.col.p, A.h_col.data(), A.nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
+  A.val.alloc_padded(A.nnz, 8);
+  A.nrb = A.ndesc = 0;
+  c.nrb_u = c.nrb_p = c.ndesc_u = c.ndesc_p = 0;
   A.max_row = 0;
   for (int64_t i = 0; i < nrows; ++i) {
     A.max_row = std::max<int>(A.max_row, (int)(rowptr[i + 1] - rowptr[i]));
@@ -104,6 +107,11 @@ int nsx_set_option(nsx_ctx *ctx, int option, int64_t value) {
         if (value != 0 && value != 1) throw std::invalid_argument("ordering must be 0 (natural) or 1 (multicolour)");
         ctx->ordering = (int)value; break;
       case NSX_OPT_VERBOSE: ctx->verbose = (int)value; break;
+      case NSX_OPT_ORTHO: ctx->ortho = value ? 1 : 0; break;
+      case NSX_OPT_COOP_SWEEP: ctx->coop_sweep = value ? 1 : 0; break;
+      case NSX_OPT_STREAM_SPMV:
+        if (value < 0 || value > 2) throw std::invalid_argument("SpMV kernel must be 0, 1 or 2");
+        ctx->stream_spmv = (int)value; break;
       default: throw std::invalid_argument("unknown option");
     }
   });
@@ -417,7 +425,7 @@ int nsx_time_kernel(nsx_ctx *ctx, int what, int reps, int flush_l2, double *ms_p
     Ctx &c = *ctx;
     need_final(c);
     if (reps < 1 || !ms_per_launch) throw std::invalid_argument("bad timing request");
-    if (flush_l2 && !c.flush.p) c.flush.alloc((size_t)256 << 20);
+    if (flush_l2 && !c.flush.p) { c.flush.alloc((size_t)512 << 20); c.flush.zero(c.stream); }
     cudaEvent_t e0, e1;
     NSX_CUDA(cudaEventCreate(&e0));
     NSX_CUDA(cudaEventCreate(&e1));
@@ -427,7 +435,7 @@ int nsx_time_kernel(nsx_ctx *ctx, int what, int reps, int flush_l2, double *ms_p
     if (what == 6 || what == 7) { P = &tri_plan(c, NSX_BLOCK_F); ilu0_factor(c, *P, c.F); }
     double total = 0;
     for (int r = 0; r < reps; ++r) {
-      if (flush_l2) NSX_CUDA(cudaMemsetAsync(c.flush.p, r & 0xff, c.flush.n, c.stream));
+      if (flush_l2) flush_l2_cache(c, r);
       NSX_CUDA(cudaEventRecord(e0, c.stream));
       switch (what) {
         case 0: block_spmv(c, x, y); break;
@@ -438,6 +446,8 @@ int nsx_time_kernel(nsx_ctx *ctx, int what, int reps, int flush_l2, double *ms_p
         case 5: sgs_apply(c, *P, y, x); break;
         case 6: ilu0_apply(c, *P, y, x); break;
         case 7: ilu0_factor(c, *P, c.F); break;
+        case 8: spmv_probe(c, c.F, 0, x, y); break;   // stream F's values + columns only
+        case 9: spmv_probe(c, c.F, 1, x, y); break;   // ... plus the x gather
         default: throw std::invalid_argument("unknown kernel id");
       }
       NSX_CUDA(cudaEventRecord(e1, c.stream));

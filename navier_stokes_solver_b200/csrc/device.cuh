@@ -47,6 +47,13 @@ struct DevBuf {
     if (count) NSX_CUDA(cudaMalloc(&p, count * sizeof(T)));
     n = count;
   }
+  // `pad` extra elements behind the `count` the buffer reports (bulk copies round their ranges up to 16 bytes)
+  void alloc_padded(size_t count, size_t pad) {
+    release();
+    NSX_CUDA(cudaMalloc(&p, (count + pad) * sizeof(T)));
+    NSX_CUDA(cudaMemset(p, 0, (count + pad) * sizeof(T)));
+    n = count;
+  }
   void upload(const T *h, size_t count, cudaStream_t s) {
     alloc(count);
     if (count) NSX_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
@@ -54,6 +61,10 @@ struct DevBuf {
   void upload(const std::vector<T> &h, cudaStream_t s) { upload(h.data(), h.size(), s); }
   void zero(cudaStream_t s) { if (n) NSX_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
 };
+
+// one row block of the TMA-fed SpMV: 16-byte aligned element ranges of the value / column arrays of the
+// one or two matrices that share rows [r0, r1): aligned start a, aligned count c, front pad o, real count n
+struct alignas(16) RowBlockDesc { long long a1, a2; int c1, o1, n1, c2, o2, n2, r0, r1, kind, lanes, pad[2]; };  // 64 bytes: bulk-copied into the ring
 
 // Device CSR block (pattern fixed once, values rewritten by every assembly).
 struct DevCSR {
@@ -63,6 +74,10 @@ struct DevCSR {
   DevBuf<int32_t> col;
   DevBuf<double> val;
   DevBuf<int32_t> diag;  // offset of the diagonal inside each row (square blocks), -1 if absent
+  DevBuf<RowBlockDesc> desc;  // row blocks of the TMA-fed SpMV
+  int ndesc = 0;
+  DevBuf<int32_t> rb;   // row blocks of the streaming SpMV (runs of rows with a bounded non-zero count)
+  int nrb = 0;
   std::vector<int64_t> h_rowptr;  // host copies of the pattern (symbolic work is done on the host)
   std::vector<int32_t> h_col;
   int max_row = 0;
@@ -86,6 +101,7 @@ struct TriPlan {
   DevBuf<double> val;                   // filtered values (SGS) or LU factors (ILU)
   DevBuf<double> work, yp;              // intermediate vectors (permuted numbering)
   bool factored = false;
+  int coop_grid = 0;                    // grid of the cooperative sweep (0: not sized yet)
   std::vector<int64_t> h_rowptr, lvl_f, lvl_b;
   std::vector<int32_t> h_col, h_diag, h_perm;
   std::vector<TriStep> steps_f, steps_b;
@@ -100,6 +116,13 @@ struct Ctx {
   std::string err;
   int verbose = 0;
   int ordering = 1;
+  int ortho = 1;        // 0 modified Gram-Schmidt chain (as deal.II), 1 batched classical Gram-Schmidt with re-orthogonalisation
+  int stream_spmv = 2;  // 2: TMA-fed persistent SpMV, 1: streaming through shared memory with plain loads, 0: sub-warp per row
+  DevBuf<RowBlockDesc> desc_u, desc_p;
+  int ndesc_u = 0, ndesc_p = 0;
+  DevBuf<int32_t> rb_u, rb_p;  // row blocks of the Jacobian block SpMV: velocity rows (F + Bt), pressure rows (B)
+  int nrb_u = 0, nrb_p = 0;
+  int coop_sweep = 1;   // multicolour sweeps as one cooperative launch with grid barriers between colours
   int num_sms = 148;
 
   // discretisation
@@ -162,7 +185,8 @@ struct Ctx {
 };
 
 // ---- kernels_vec.cu -------------------------------------------------------------------------
-constexpr int RED_SLOTS = 64;  // device scalar slots
+constexpr int RED_SLOTS = 192;  // device scalar slots: 80 per solver nesting depth + scratch
+struct VecList { const double *v[32]; };
 void vec_copy(Ctx &c, double *y, const double *x, int64_t n);
 void vec_set(Ctx &c, double *y, double a, int64_t n);
 void vec_scale(Ctx &c, double *y, double a, int64_t n);
@@ -177,10 +201,14 @@ void vec_dot_dev(Ctx &c, int slot, const double *a, const double *b, int64_t n);
 // w += (sign * *dev_coef) x ; slot <- w . v      (deal.II add_and_dot; v may alias w)
 void vec_add_and_dot_dev(Ctx &c, int slot, double *w, double sign, const double *dev_coef, const double *x, const double *v, int64_t n);
 double *slot_ptr(Ctx &c, int slot);
+// batched classical Gram-Schmidt pass: slot0+m <- v_m . w (m < k) ; then w -= sum_m slot[m] v_m, slot_norm <- w . w
+void vec_multi_dot_dev(Ctx &c, int slot0, const VecList &V, int k, const double *w, int64_t n);
+void vec_multi_axpy_norm_dev(Ctx &c, int slot_norm, const VecList &V, int k, int slot_coef, double *w, int64_t n);
 // blocking reads of device scalars
 double read_slot(Ctx &c, int slot);
 void read_slots(Ctx &c, int first, int count, double *out);
 double vec_dot(Ctx &c, const double *a, const double *b, int64_t n);
+void flush_l2_cache(Ctx &c, int round);
 double vec_norm(Ctx &c, const double *a, int64_t n);
 double vec_add_and_dot(Ctx &c, double *w, double a, const double *x, const double *v, int64_t n);
 
@@ -188,6 +216,7 @@ double vec_add_and_dot(Ctx &c, double *w, double a, const double *x, const doubl
 void spmv(Ctx &c, const DevCSR &A, const double *x, double *y, bool add = false);
 void block_spmv(Ctx &c, const double *x, double *y);  // y_u = F x_u + Bt x_p ; y_p = B x_u
 void extract_diag(Ctx &c, const DevCSR &A, double *d, double *dinv);
+void spmv_probe(Ctx &c, const DevCSR &A, int what, const double *x, double *sink);  // measurement only
 
 // ---- assemble.cu ----------------------------------------------------------------------------
 void build_assembly_maps(Ctx &c);

@@ -10,6 +10,8 @@
 // arrays (coalesced, streamed with ld.global.cs so that x stays cached), x is gathered through
 // the read-only path, and the row sum is a log2(G) shuffle reduction (deterministic order).
 // Algorithmic bytes per product: 12 nnz + 8 (m+1) + 8 n + 8 m.
+#include <algorithm>
+
 #include "device.cuh"
 
 namespace nsx {
@@ -81,6 +83,280 @@ __global__ void k_extract_diag(int64_t n, const int64_t *__restrict__ rowptr, co
   if (dinv) dinv[i] = 1.0 / v;
 }
 
+// ---- streaming kernel ------------------------------------------------------------------------
+// A CTA owns a run of consecutive rows holding at most SNNZ non-zeros (of one matrix, or of the two
+// matrices that share those rows: F and Bt).  Phase 1 streams the run's values and columns with
+// fully coalesced, independent loads (SNNZ / ST per thread in flight) and parks val * x[col] in
+// shared memory; phase 2 reduces each row's segment with a sub-warp.  The HBM stream is decoupled
+// from the row structure, so short rows (Bt: 13, Mp: 16 per row) stream as well as long ones.
+constexpr int ST = 256;      // threads per CTA
+constexpr int SNNZ = 2048;   // non-zeros per CTA
+constexpr int SG = 8;        // lanes per row in the reduction phase
+constexpr int SROWS = 256;   // rows per CTA at most (their row pointers are staged in shared memory)
+
+struct StreamMat {
+  const int64_t *rp;
+  const int32_t *col;
+  const double *val;
+  const double *x;
+};
+
+__device__ __forceinline__ void stream_rows(const int32_t *__restrict__ rb, int b, const StreamMat &A1, const StreamMat &A2, bool two,
+                                            double *__restrict__ y, int add, double *prod, int *srp) {
+  const int r0 = rb[b], r1 = rb[b + 1], nr = r1 - r0;
+  const int64_t s1 = A1.rp[r0];
+  const int n1 = (int)(A1.rp[r1] - s1);
+  int64_t s2 = 0;
+  int n2 = 0;
+  if (two) { s2 = A2.rp[r0]; n2 = (int)(A2.rp[r1] - s2); }
+  // row pointers of the block (relative), loaded alongside the streams so that phase 2 touches no global memory
+  for (int i = threadIdx.x; i <= nr; i += ST) {
+    srp[i] = (int)(A1.rp[r0 + i] - s1);
+    if (two) srp[SROWS + 1 + i] = n1 + (int)(A2.rp[r0 + i] - s2);
+  }
+#pragma unroll 8
+  for (int k = threadIdx.x; k < n1; k += ST) prod[k] = __ldcs(A1.val + s1 + k) * __ldg(A1.x + __ldcs(A1.col + s1 + k));
+  if (two) {
+#pragma unroll 2
+    for (int k = threadIdx.x; k < n2; k += ST) prod[n1 + k] = __ldcs(A2.val + s2 + k) * __ldg(A2.x + __ldcs(A2.col + s2 + k));
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & (SG - 1);
+  const int passes = (nr + ST / SG - 1) / (ST / SG);
+  for (int ps = 0; ps < passes; ++ps) {
+    const int i = ps * (ST / SG) + threadIdx.x / SG;
+    double s = 0;
+    if (i < nr) {
+      for (int k = srp[i] + lane; k < srp[i + 1]; k += SG) s += prod[k];
+      if (two)
+        for (int k = srp[SROWS + 1 + i] + lane; k < srp[SROWS + 2 + i]; k += SG) s += prod[k];
+    }
+#pragma unroll
+    for (int o = SG / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, SG);
+    if (i < nr && lane == 0) y[r0 + i] = add ? y[r0 + i] + s : s;
+  }
+}
+
+__global__ void __launch_bounds__(ST) k_spmv_stream(const int32_t *__restrict__ rb, StreamMat A, double *__restrict__ y, int add) {
+  __shared__ double prod[SNNZ];
+  __shared__ int srp[2 * (SROWS + 1)];
+  stream_rows(rb, blockIdx.x, A, A, false, y, add, prod, srp);
+}
+
+// jacobian_matrix.vmult in one launch: CTAs [0, nb_u) own velocity rows (F and Bt), the rest own pressure rows (B)
+__global__ void __launch_bounds__(ST) k_block_spmv_stream(const int32_t *__restrict__ rb_u, int nb_u, StreamMat F, StreamMat Bt,
+                                                          const int32_t *__restrict__ rb_p, StreamMat B, double *__restrict__ y, int64_t n_u) {
+  __shared__ double prod[SNNZ];
+  __shared__ int srp[2 * (SROWS + 1)];
+  if ((int)blockIdx.x < nb_u) stream_rows(rb_u, blockIdx.x, F, Bt, true, y, 0, prod, srp);
+  else stream_rows(rb_p, blockIdx.x - nb_u, B, B, false, y + n_u, 0, prod, srp);
+}
+
+// rows grouped into runs of at most SNNZ non-zeros (summed over the one or two matrices sharing the rows)
+void build_row_blocks(Ctx &c, const DevCSR &A1, const DevCSR *A2, DevBuf<int32_t> &rb, int &nb) {
+  std::vector<int32_t> h{0};
+  int64_t acc = 0;
+  for (int64_t r = 0; r < A1.nrows; ++r) {
+    int64_t len = A1.h_rowptr[r + 1] - A1.h_rowptr[r];
+    if (A2) len += A2->h_rowptr[r + 1] - A2->h_rowptr[r];
+    if (len > SNNZ) throw std::runtime_error("matrix row too long for the streaming SpMV");
+    if (acc + len > SNNZ || r - h.back() >= SROWS) { h.push_back((int32_t)r); acc = 0; }
+    acc += len;
+  }
+  h.push_back((int32_t)A1.nrows);
+  nb = (int)h.size() - 1;
+  rb.upload(h, c.stream);
+}
+
+// ---- TMA-fed persistent kernel ----------------------------------------------------------------
+// The same two phases, but the value / column streams are brought into shared memory by the TMA
+// engine (cp.async.bulk, 1-D bulk copies completing on an mbarrier) through a TS-stage ring that a
+// dedicated producer warp keeps full.  The HBM stream no longer depends on how long the consumer
+// warps stall on the x gather: up to (TS-1) x 24 KB per CTA are in flight at any time.  One
+// persistent CTA pair per SM walks the row blocks grid-strided.
+constexpr int TS = 3;                 // ring stages
+constexpr int TNNZ = 1024;            // non-zeros per row block
+constexpr int TROWS = 128;            // rows per row block at most
+constexpr int TCAP = TNNZ + 16;       // elements per stage (two segments, each padded to a multiple of 4 at both ends)
+constexpr int TRP = TROWS + 4;        // row pointers per matrix per stage (range padded to even ends)
+constexpr int TCONS = 256;            // consumer threads (8 warps) + 1 producer warp
+constexpr size_t TMA_STAGE = (size_t)TCAP * 12 + 2 * TRP * 8 + sizeof(RowBlockDesc);  // values, columns, row pointers, descriptor
+constexpr size_t TMA_SMEM = TS * TMA_STAGE + 2 * TS * 8;  // ring + (full, empty) barriers
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (unsigned spins = 0; !ok; ++spins) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (spins > (1u << 24)) __trap();  // a broken pipeline must fail loudly, not hang the device
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct TmaStage {  // views into one stage of the ring
+  double *val; int32_t *col; int64_t *rp1, *rp2; const RowBlockDesc *desc;
+};
+__device__ __forceinline__ TmaStage stage_of(unsigned char *ring, int st) {
+  unsigned char *b = ring + (size_t)st * TMA_STAGE;
+  TmaStage s;
+  s.val = (double *)b;
+  s.rp1 = (int64_t *)(b + (size_t)TCAP * 8);
+  s.rp2 = s.rp1 + TRP;
+  s.col = (int32_t *)(b + (size_t)TCAP * 8 + 2 * TRP * 8);
+  s.desc = (const RowBlockDesc *)(b + (size_t)TCAP * 12 + 2 * TRP * 8);
+  return s;
+}
+
+// Row blocks `first, first + stride, ...` of a list whose entries are of kind 0 (matrices M[0] and, if it has
+// non-zeros there, M[1] share the rows; y offset 0) or kind 1 (matrix M[2] alone; y offset yoff1).
+__device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, int first, int stride, int nb, const StreamMat *M,
+                                         double *__restrict__ y, int64_t yoff1, int add, unsigned char *ring, uint64_t *full, uint64_t *empty,
+                                         RowBlockDesc *pdesc) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nit = first < nb ? (nb - first + stride - 1) / stride : 0;
+  if (tid >= TCONS) {
+    // producer warp: descriptors are fetched 32 at a time by the whole warp, lane 0 feeds the ring
+    for (int it0 = 0; it0 < nit; it0 += 32) {
+      __syncwarp();
+      if (it0 + lane < nit) pdesc[lane] = desc[first + (it0 + lane) * stride];
+      __syncwarp();
+      if (lane == 0)
+        for (int it = it0; it < min(nit, it0 + 32); ++it) {
+          const int st = it % TS, use = it / TS;
+          if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
+          const RowBlockDesc d = pdesc[it - it0];
+          const StreamMat &A1 = M[d.kind ? 2 : 0], &A2 = M[1];
+          const bool two = d.kind == 0 && d.c2 > 0;
+          const TmaStage S = stage_of(ring, st);
+          const int ra = d.r0 & ~1, rc = ((d.r1 + 2) & ~1) - ra;  // even-aligned range of row pointers covering [r0, r1]
+          mbar_expect_tx(&full[st], (uint32_t)(d.c1 + (two ? d.c2 : 0)) * 12u + (uint32_t)rc * 8u * (two ? 2u : 1u) + (uint32_t)sizeof(RowBlockDesc));
+          bulk_g2s((void *)S.desc, desc + first + it * stride, sizeof(RowBlockDesc), &full[st]);
+          bulk_g2s(S.rp1, A1.rp + ra, rc * 8, &full[st]);
+          if (d.c1) {
+            bulk_g2s(S.val, A1.val + d.a1, d.c1 * 8, &full[st]);
+            bulk_g2s(S.col, A1.col + d.a1, d.c1 * 4, &full[st]);
+          }
+          if (two) {
+            bulk_g2s(S.rp2, A2.rp + ra, rc * 8, &full[st]);
+            bulk_g2s(S.val + d.c1, A2.val + d.a2, d.c2 * 8, &full[st]);
+            bulk_g2s(S.col + d.c1, A2.col + d.a2, d.c2 * 4, &full[st]);
+          }
+        }
+    }
+    return;
+  }
+  for (int it = 0; it < nit; ++it) {
+    const int st = it % TS, use = it / TS;
+    const TmaStage S = stage_of(ring, st);
+    mbar_wait(&full[st], use & 1);
+    const RowBlockDesc d = *S.desc;
+    const bool two = d.kind == 0 && d.c2 > 0;
+    const double *__restrict__ x1 = M[d.kind ? 2 : 0].x, *__restrict__ x2 = M[1].x;
+    double *v = S.val;
+    const int32_t *cidx = S.col;
+    // phase 1: products in place (every consumer thread busy, four independent gathers each)
+#pragma unroll 4
+    for (int k = d.o1 + tid; k < d.o1 + d.n1; k += TCONS) v[k] *= __ldg(x1 + cidx[k]);
+    if (two) {
+#pragma unroll 2
+      for (int k = d.c1 + d.o2 + tid; k < d.c1 + d.o2 + d.n2; k += TCONS) v[k] *= __ldg(x2 + cidx[k]);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // phase 2: a sub-warp of SG lanes reduces each row's segment(s); row pointers come from the stage
+    constexpr int L = SG;
+    const int sl = tid & (L - 1);
+    const int64_t s1 = d.a1, s2 = d.a2 - d.c1;  // stage index = global index - s
+    const int nr = d.r1 - d.r0, rpp = TCONS / L, passes = (nr + rpp - 1) / rpp, roff = d.r0 & 1;
+    double *yy = y + (d.kind ? yoff1 : 0);
+    for (int ps = 0; ps < passes; ++ps) {
+      const int i = ps * rpp + tid / L;
+      double s = 0;
+      if (i < nr) {
+        const int b1 = (int)(S.rp1[roff + i] - s1), e1 = (int)(S.rp1[roff + i + 1] - s1);
+        for (int k = b1 + sl; k < e1; k += L) s += v[k];
+        if (two) {
+          const int b2 = (int)(S.rp2[roff + i] - s2), e2 = (int)(S.rp2[roff + i + 1] - s2);
+          for (int k = b2 + sl; k < e2; k += L) s += v[k];
+        }
+      }
+#pragma unroll
+      for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, L);
+      if (i < nr && sl == 0) yy[d.r0 + i] = add ? yy[d.r0 + i] + s : s;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes (products) before the TMA's next write
+    // release the stage (this warp's reads are done; the mbarrier orders them before the TMA's next write)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+}
+
+// y = A x (kind-0 blocks with one matrix), or jacobian_matrix.vmult with M = {F, Bt, B}: the row blocks of the
+// velocity rows (F + Bt, kind 0) come first in the list, then those of the pressure rows (B, kind 1)
+__global__ void __launch_bounds__(TCONS + 32, 4) k_spmv_tma(const RowBlockDesc *__restrict__ desc, int nb, StreamMat M0, StreamMat M1, StreamMat M2,
+                                                            double *__restrict__ y, int64_t yoff1, int add) {
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  __shared__ RowBlockDesc pdesc[32];
+  __shared__ StreamMat M[3];
+  uint64_t *full = (uint64_t *)(tma_smem + TS * TMA_STAGE), *empty = full + TS;
+  if (threadIdx.x == 0) {
+    M[0] = M0; M[1] = M1; M[2] = M2;
+    for (int s = 0; s < TS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TCONS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  tma_rows(desc, blockIdx.x, gridDim.x, nb, M, y, yoff1, add, tma_smem, full, empty, pdesc);
+}
+
+void append_row_descs(std::vector<RowBlockDesc> &h, const DevCSR &A1, const DevCSR *A2, int kind) {
+  int64_t acc = 0;
+  int64_t r0 = 0;
+  auto close = [&](int64_t r1) {
+    if (r1 == r0) return;
+    RowBlockDesc d{};
+    const int64_t s1 = A1.h_rowptr[r0], e1 = A1.h_rowptr[r1];
+    d.a1 = s1 & ~(int64_t)3; d.o1 = (int)(s1 - d.a1); d.n1 = (int)(e1 - s1);
+    d.c1 = d.n1 ? (int)(((e1 + 3) & ~(int64_t)3) - d.a1) : 0;
+    if (A2) {
+      const int64_t s2 = A2->h_rowptr[r0], e2 = A2->h_rowptr[r1];
+      d.a2 = s2 & ~(int64_t)3; d.o2 = (int)(s2 - d.a2); d.n2 = (int)(e2 - s2);
+      d.c2 = d.n2 ? (int)(((e2 + 3) & ~(int64_t)3) - d.a2) : 0;
+    }
+    d.r0 = (int)r0; d.r1 = (int)r1; d.kind = kind;
+    const double mean = (double)(d.n1 + d.n2) / (double)(r1 - r0);
+    d.lanes = mean >= 12 ? 8 : 4;
+    h.push_back(d);
+    r0 = r1;
+  };
+  for (int64_t r = 0; r < A1.nrows; ++r) {
+    int64_t len = A1.h_rowptr[r + 1] - A1.h_rowptr[r];
+    if (A2) len += A2->h_rowptr[r + 1] - A2->h_rowptr[r];
+    if (len > TNNZ) throw std::runtime_error("matrix row too long for the TMA-fed SpMV");
+    if (acc + len > TNNZ || r - r0 >= TROWS) { close(r); acc = 0; }
+    acc += len;
+  }
+  close(A1.nrows);
+}
+
+void tma_attr_once() {
+  static bool done = false;
+  if (done) return;
+  NSX_CUDA(cudaFuncSetAttribute(k_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+  done = true;
+}
+
 inline int pick_group(const DevCSR &A) {
   const double avg = A.nrows ? (double)A.nnz / (double)A.nrows : 0.0;
   if (avg > 48) return 16;
@@ -90,8 +366,29 @@ inline int pick_group(const DevCSR &A) {
 
 }  // namespace
 
-void spmv(Ctx &c, const DevCSR &A, const double *x, double *y, bool add) {
+void spmv(Ctx &c, const DevCSR &A_, const double *x, double *y, bool add) {
+  DevCSR &A = const_cast<DevCSR &>(A_);
   if (!A.nrows) return;
+  if (c.stream_spmv == 2 && !A.h_rowptr.empty() && A.nrows < (int64_t)1 << 31) {
+    tma_attr_once();
+    if (!A.ndesc) {
+      std::vector<RowBlockDesc> h;
+      append_row_descs(h, A, nullptr, 0);
+      A.ndesc = (int)h.size();
+      A.desc.upload(h, c.stream);
+    }
+    const int grid = std::min(A.ndesc, 4 * c.num_sms);
+    const StreamMat M{A.rowptr.p, A.col.p, A.val.p, x};
+    k_spmv_tma<<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0);
+    c.stat_launches++; c.stat_spmv++;
+    return;
+  }
+  if (c.stream_spmv && !A.h_rowptr.empty() && A.nrows < (int64_t)1 << 31) {
+    if (!A.nrb) build_row_blocks(c, A, nullptr, A.rb, A.nrb);
+    k_spmv_stream<<<A.nrb, ST, 0, c.stream>>>(A.rb.p, StreamMat{A.rowptr.p, A.col.p, A.val.p, x}, y, add ? 1 : 0);
+    c.stat_launches++; c.stat_spmv++;
+    return;
+  }
   const int G = pick_group(A);
   const int64_t threads = A.nrows * G;
   const int grid = (int)((threads + 255) / 256);
@@ -103,6 +400,30 @@ void spmv(Ctx &c, const DevCSR &A, const double *x, double *y, bool add) {
 
 void block_spmv(Ctx &c, const double *x, double *y) {
   const int64_t n = c.n_u + c.n_p;
+  if (c.stream_spmv == 2 && n < (int64_t)1 << 31) {
+    tma_attr_once();
+    if (!c.ndesc_u) {
+      std::vector<RowBlockDesc> h;
+      append_row_descs(h, c.F, &c.Bt, 0);
+      append_row_descs(h, c.B, nullptr, 1);
+      c.ndesc_u = (int)h.size();
+      c.desc_u.upload(h, c.stream);
+    }
+    const int grid = std::min(c.ndesc_u, 4 * c.num_sms);
+    k_spmv_tma<<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(c.desc_u.p, c.ndesc_u, StreamMat{c.F.rowptr.p, c.F.col.p, c.F.val.p, x},
+                                                         StreamMat{c.Bt.rowptr.p, c.Bt.col.p, c.Bt.val.p, x + c.n_u},
+                                                         StreamMat{c.B.rowptr.p, c.B.col.p, c.B.val.p, x}, y, c.n_u, 0);
+    c.stat_launches++; c.stat_spmv++;
+    return;
+  }
+  if (c.stream_spmv && n < (int64_t)1 << 31) {
+    if (!c.nrb_u) { build_row_blocks(c, c.F, &c.Bt, c.rb_u, c.nrb_u); build_row_blocks(c, c.B, nullptr, c.rb_p, c.nrb_p); }
+    k_block_spmv_stream<<<c.nrb_u + c.nrb_p, ST, 0, c.stream>>>(c.rb_u.p, c.nrb_u, StreamMat{c.F.rowptr.p, c.F.col.p, c.F.val.p, x},
+                                                                StreamMat{c.Bt.rowptr.p, c.Bt.col.p, c.Bt.val.p, x + c.n_u}, c.rb_p.p,
+                                                                StreamMat{c.B.rowptr.p, c.B.col.p, c.B.val.p, x}, y, c.n_u);
+    c.stat_launches++; c.stat_spmv++;
+    return;
+  }
   const double avg = (double)(c.F.nnz + c.Bt.nnz + c.B.nnz) / (double)n;
   if (avg > 40) {
     const int grid = (int)((n * 16 + 255) / 256);
@@ -114,6 +435,33 @@ void block_spmv(Ctx &c, const double *x, double *y) {
                                                  c.B.rowptr.p, c.B.col.p, c.B.val.p, x, y);
   }
   c.stat_launches++; c.stat_spmv++;
+}
+
+// ---- probes: upper bounds for the SpMV on this matrix (measurement only) ----------------------
+namespace {
+// what 0: stream val + col only ; 1: + gather x[col] ; both reduce everything into one number per thread
+template <int WHAT>
+__global__ void __launch_bounds__(256) k_probe(int64_t nnz, const int32_t *__restrict__ col, const double *__restrict__ val,
+                                               const double *__restrict__ x, double *sink) {
+  double acc = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; k + 3 * stride < nnz; k += 4 * stride) {
+    const double v0 = __ldcs(val + k), v1 = __ldcs(val + k + stride), v2 = __ldcs(val + k + 2 * stride), v3 = __ldcs(val + k + 3 * stride);
+    const int32_t c0 = __ldcs(col + k), c1 = __ldcs(col + k + stride), c2 = __ldcs(col + k + 2 * stride), c3 = __ldcs(col + k + 3 * stride);
+    if (WHAT == 0) acc += v0 * c0 + v1 * c1 + v2 * c2 + v3 * c3;
+    else acc += v0 * __ldg(x + c0) + v1 * __ldg(x + c1) + v2 * __ldg(x + c2) + v3 * __ldg(x + c3);
+  }
+  for (; k < nnz; k += stride) acc += __ldcs(val + k) * (WHAT == 0 ? (double)__ldcs(col + k) : __ldg(x + __ldcs(col + k)));
+  if (acc == 1.2345e-300) *sink = acc;
+}
+}  // namespace
+
+void spmv_probe(Ctx &c, const DevCSR &A, int what, const double *x, double *sink) {
+  const int grid = c.num_sms * 8;
+  if (what == 0) k_probe<0><<<grid, 256, 0, c.stream>>>(A.nnz, A.col.p, A.val.p, x, sink);
+  else k_probe<1><<<grid, 256, 0, c.stream>>>(A.nnz, A.col.p, A.val.p, x, sink);
+  c.stat_launches++;
 }
 
 void extract_diag(Ctx &c, const DevCSR &A, double *d, double *dinv) {

@@ -92,6 +92,99 @@ __global__ void __launch_bounds__(VT) k_dot(const double *__restrict__ a, const 
 
 inline int vgrid(Ctx &c, int64_t n) { return grid_for(n, VT * 4, c.num_sms * 8); }
 
+// ---- batched classical Gram-Schmidt: all projections of one pass in two kernels -------------
+constexpr int MD = 8;  // vectors per register chunk of the multi-dot
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// result[m] = v_m . w for m < k  (k <= 31)
+__global__ void __launch_bounds__(VT) k_multi_dot(VecList V, int k, const double *__restrict__ w, int64_t n, double *partial,
+                                                  unsigned int *counter, double *result) {
+  __shared__ const double *sv[32];
+  __shared__ double sh[VT / 32][MD];
+  __shared__ bool last;
+  if (threadIdx.x < 32) sv[threadIdx.x] = V.v[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  for (int c0 = 0; c0 < k; c0 += MD) {
+    double acc[MD];
+#pragma unroll
+    for (int m = 0; m < MD; ++m) acc[m] = 0.0;
+    const int kc = min(MD, k - c0);
+    for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT) {
+      const double wi = w[i];
+#pragma unroll
+      for (int m = 0; m < MD; ++m)
+        if (m < kc) acc[m] += wi * sv[c0 + m][i];
+    }
+#pragma unroll
+    for (int m = 0; m < MD; ++m) {
+      const double r = warp_sum(acc[m]);
+      if (lane == 0) sh[wp][m] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < kc) {
+      double r = 0;
+#pragma unroll
+      for (int q = 0; q < VT / 32; ++q) r += sh[q][threadIdx.x];
+      partial[(size_t)blockIdx.x * 32 + c0 + threadIdx.x] = r;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicInc(counter, gridDim.x - 1);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    for (int m = wp; m < k; m += VT / 32) {
+      double r = 0;
+      for (int b = lane; b < gridDim.x; b += 32) r += __ldcg(&partial[(size_t)b * 32 + m]);
+      r = warp_sum(r);
+      if (lane == 0) result[m] = r;
+    }
+  }
+}
+
+// w -= sum_m coef[m] v_m ; *norm2 = w . w
+__global__ void __launch_bounds__(VT) k_multi_axpy_norm(VecList V, int k, const double *coef, double *__restrict__ w, int64_t n, double *partial,
+                                                        unsigned int *counter, double *norm2) {
+  __shared__ const double *sv[32];
+  __shared__ double sc[32];
+  __shared__ double sh[VT / 32];
+  __shared__ bool last;
+  if (threadIdx.x < 32) { sv[threadIdx.x] = V.v[threadIdx.x]; sc[threadIdx.x] = threadIdx.x < k ? coef[threadIdx.x] : 0.0; }
+  __syncthreads();
+  double acc = 0;
+  for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT) {
+    double wi = w[i];
+    for (int m = 0; m < k; ++m) wi -= sc[m] * sv[m][i];
+    w[i] = wi;
+    acc += wi * wi;
+  }
+  const double s = block_sum(acc, sh);
+  if (threadIdx.x == 0) {
+    partial[(size_t)blockIdx.x * 32] = s;
+    __threadfence();
+    const unsigned int t = atomicInc(counter, gridDim.x - 1);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double r = 0;
+    for (int i = threadIdx.x; i < gridDim.x; i += VT) r += __ldcg(&partial[(size_t)i * 32]);
+    r = block_sum(r, sh);
+    if (threadIdx.x == 0) *norm2 = r;
+  }
+}
+
 }  // namespace
 
 #define LAUNCHED(c) ((c).stat_launches++)
@@ -131,9 +224,23 @@ void vec_equ(Ctx &c, double *y, double a, const double *x, int64_t n) {
 
 double *slot_ptr(Ctx &c, int slot) { return c.red_result.p + slot; }
 
+static void ensure_red(Ctx &c);
+
+void vec_multi_dot_dev(Ctx &c, int slot0, const VecList &V, int k, const double *w, int64_t n) {
+  ensure_red(c);
+  if (k < 1 || k > 31) throw std::invalid_argument("multi-dot handles 1..31 vectors");
+  k_multi_dot<<<vgrid(c, n), VT, 0, c.stream>>>(V, k, w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot0));
+  LAUNCHED(c);
+}
+void vec_multi_axpy_norm_dev(Ctx &c, int slot_norm, const VecList &V, int k, int slot_coef, double *w, int64_t n) {
+  ensure_red(c);
+  k_multi_axpy_norm<<<vgrid(c, n), VT, 0, c.stream>>>(V, k, slot_ptr(c, slot_coef), w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot_norm));
+  LAUNCHED(c);
+}
+
 static void ensure_red(Ctx &c) {
   if (!c.red_partial.p) {
-    c.red_partial.alloc(RED_MAX_BLOCKS);
+    c.red_partial.alloc((size_t)RED_MAX_BLOCKS * 32);
     c.red_result.alloc(RED_SLOTS);
     c.red_result.zero(c.stream);
     c.red_counter.alloc(1);
@@ -166,6 +273,20 @@ void read_slots(Ctx &c, int first, int count, double *out) {
   NSX_CUDA(cudaStreamSynchronize(c.stream));
   for (int i = 0; i < count; ++i) out[i] = c.h_scalars[first + i];
 }
+// L2 flush between timed launches: write 256 MiB (evicts everything, leaves dirty lines), then read
+// another 256 MiB so that the lines the timed kernel evicts are clean -- otherwise the kernel under
+// test pays the write-back of the flush itself.
+__global__ void k_flush_read(const int4 *__restrict__ p, int64_t n, int *sink) {
+  int acc = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc ^= __ldcg(p + i).x;
+  if (acc == 0x5a5a5a5a) *sink = acc;
+}
+void flush_l2_cache(Ctx &c, int round) {
+  const size_t half = c.flush.n / 2;
+  NSX_CUDA(cudaMemsetAsync(c.flush.p, round & 0xff, half, c.stream));
+  k_flush_read<<<c.num_sms * 8, 256, 0, c.stream>>>((const int4 *)(c.flush.p + half), (int64_t)(half / sizeof(int4)), (int *)c.flush.p);
+}
+
 double vec_dot(Ctx &c, const double *a, const double *b, int64_t n) {
   vec_dot_dev(c, RED_SLOTS - 1, a, b, n);
   return read_slot(c, RED_SLOTS - 1);

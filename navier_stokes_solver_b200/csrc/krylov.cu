@@ -123,7 +123,7 @@ void solver_fgmres(Ctx &c, Control &ctl, const DOp &A, double *x, const double *
   std::vector<std::vector<double>> H(basis_size, std::vector<double>(basis_size + 1, 0.0));
   std::vector<double> y;
   std::vector<char> z_used(basis_size, 0);
-  double hs[32];
+  double hs[80];
   int accumulated_iterations = 0;
   double res = -std::numeric_limits<double>::max();
   double *aux = W.vec(0);
@@ -146,12 +146,24 @@ void solver_fgmres(Ctx &c, Control &ctl, const DOp &A, double *x, const double *
       if (!z_used[j]) { vec_set(c, z(j), 0.0, n); z_used[j] = 1; }
       M(z(j), v(j));
       A(aux, z(j));
-      vec_dot_dev(c, slot0, aux, v(0), n);
-      for (int i = 1; i <= j; ++i) vec_add_and_dot_dev(c, slot0 + i, aux, -1.0, slot_ptr(c, slot0 + i - 1), v(i - 1), v(i), n);
-      vec_add_and_dot_dev(c, slot0 + j + 1, aux, -1.0, slot_ptr(c, slot0 + j), v(j), aux, n);
-      read_slots(c, slot0, j + 2, hs);
-      for (int i = 0; i <= j; ++i) H[j][i] = hs[i];
-      H[j][j + 1] = a = std::sqrt(hs[j + 1]);
+      if (c.ortho == 0) {  // modified Gram-Schmidt chain, the arithmetic of deal.II's SolverFGMRES
+        vec_dot_dev(c, slot0, aux, v(0), n);
+        for (int i = 1; i <= j; ++i) vec_add_and_dot_dev(c, slot0 + i, aux, -1.0, slot_ptr(c, slot0 + i - 1), v(i - 1), v(i), n);
+        vec_add_and_dot_dev(c, slot0 + j + 1, aux, -1.0, slot_ptr(c, slot0 + j), v(j), aux, n);
+        read_slots(c, slot0, j + 2, hs);
+        for (int i = 0; i <= j; ++i) H[j][i] = hs[i];
+        H[j][j + 1] = a = std::sqrt(hs[j + 1]);
+      } else {  // two passes of batched classical Gram-Schmidt: 4 launches and one host read per column
+        VecList V;
+        for (int i = 0; i <= j; ++i) V.v[i] = v(i);
+        vec_multi_dot_dev(c, slot0, V, j + 1, aux, n);
+        vec_multi_axpy_norm_dev(c, slot0 + 64, V, j + 1, slot0, aux, n);
+        vec_multi_dot_dev(c, slot0 + 32, V, j + 1, aux, n);
+        vec_multi_axpy_norm_dev(c, slot0 + 65, V, j + 1, slot0 + 32, aux, n);
+        read_slots(c, slot0, 66, hs);
+        for (int i = 0; i <= j; ++i) H[j][i] = hs[i] + hs[32 + i];
+        H[j][j + 1] = a = std::sqrt(hs[65]);
+      }
       if (j > 0) {
         res = hessenberg_least_squares(H, j, beta, y);
         state = ctl.check(++accumulated_iterations, res);
@@ -171,7 +183,7 @@ void solver_gmres(Ctx &c, Control &ctl, const DOp &A, double *x, const double *b
   std::vector<std::vector<double>> H(n_tmp - 1, std::vector<double>(n_tmp, 0.0));
   std::vector<double> gamma(n_tmp), ci(n_tmp - 1), si(n_tmp - 1), h(n_tmp - 1);
   std::vector<char> used(n_tmp, 0);
-  double hs[32];
+  double hs[80];
   int accumulated_iterations = 0, dim = 0;
   State state = ITERATE;
   double last_res = -std::numeric_limits<double>::max();
@@ -200,27 +212,40 @@ void solver_gmres(Ctx &c, Control &ctl, const DOp &A, double *x, const double *b
       A(p, tmp(inner));
       M(vv, p);
       dim = inner + 1;
-      double norm_vv_start = 0;
-      const bool consider = (re_orthogonalize == false) && (accumulated_iterations % 5 == 0);
-      if (consider) norm_vv_start = vec_norm(c, vv, n);
-      vec_dot_dev(c, slot0, vv, tmp(0), n);
-      for (int i = 1; i < dim; ++i) vec_add_and_dot_dev(c, slot0 + i, vv, -1.0, slot_ptr(c, slot0 + i - 1), tmp(i - 1), tmp(i), n);
-      vec_add_and_dot_dev(c, slot0 + dim, vv, -1.0, slot_ptr(c, slot0 + dim - 1), tmp(dim - 1), vv, n);
-      read_slots(c, slot0, dim + 1, hs);
-      for (int i = 0; i < dim; ++i) h[i] = hs[i];
-      double norm_vv = std::sqrt(hs[dim]);
-      bool done = false;
-      if (consider) {
-        if (norm_vv > 10. * norm_vv_start * std::sqrt(std::numeric_limits<double>::epsilon())) done = true;
-        else re_orthogonalize = true;
-      }
-      if (!done && re_orthogonalize) {
+      double norm_vv = 0;
+      if (c.ortho == 0) {
+        double norm_vv_start = 0;
+        const bool consider = (re_orthogonalize == false) && (accumulated_iterations % 5 == 0);
+        if (consider) norm_vv_start = vec_norm(c, vv, n);
         vec_dot_dev(c, slot0, vv, tmp(0), n);
         for (int i = 1; i < dim; ++i) vec_add_and_dot_dev(c, slot0 + i, vv, -1.0, slot_ptr(c, slot0 + i - 1), tmp(i - 1), tmp(i), n);
         vec_add_and_dot_dev(c, slot0 + dim, vv, -1.0, slot_ptr(c, slot0 + dim - 1), tmp(dim - 1), vv, n);
         read_slots(c, slot0, dim + 1, hs);
-        for (int i = 0; i < dim; ++i) h[i] += hs[i];
+        for (int i = 0; i < dim; ++i) h[i] = hs[i];
         norm_vv = std::sqrt(hs[dim]);
+        bool done = false;
+        if (consider) {
+          if (norm_vv > 10. * norm_vv_start * std::sqrt(std::numeric_limits<double>::epsilon())) done = true;
+          else re_orthogonalize = true;
+        }
+        if (!done && re_orthogonalize) {
+          vec_dot_dev(c, slot0, vv, tmp(0), n);
+          for (int i = 1; i < dim; ++i) vec_add_and_dot_dev(c, slot0 + i, vv, -1.0, slot_ptr(c, slot0 + i - 1), tmp(i - 1), tmp(i), n);
+          vec_add_and_dot_dev(c, slot0 + dim, vv, -1.0, slot_ptr(c, slot0 + dim - 1), tmp(dim - 1), vv, n);
+          read_slots(c, slot0, dim + 1, hs);
+          for (int i = 0; i < dim; ++i) h[i] += hs[i];
+          norm_vv = std::sqrt(hs[dim]);
+        }
+      } else {
+        VecList V;
+        for (int i = 0; i < dim; ++i) V.v[i] = tmp(i);
+        vec_multi_dot_dev(c, slot0, V, dim, vv, n);
+        vec_multi_axpy_norm_dev(c, slot0 + 64, V, dim, slot0, vv, n);
+        vec_multi_dot_dev(c, slot0 + 32, V, dim, vv, n);
+        vec_multi_axpy_norm_dev(c, slot0 + 65, V, dim, slot0 + 32, vv, n);
+        read_slots(c, slot0, 66, hs);
+        for (int i = 0; i < dim; ++i) h[i] = hs[i] + hs[32 + i];
+        norm_vv = std::sqrt(hs[65]);
       }
       const double s = norm_vv;
       h[inner + 1] = s;
@@ -353,7 +378,7 @@ struct Preconditioner {
     const double *su = src, *sp = src + nu;
     double *du = dst, *dp = dst + nu;
     Work WF(c, c.work_inner_u, nu), WP(c, c.work_inner_p, np);
-    const int slot_inner = 32;
+    const int slot_inner = 80;
     c.stat_applies++;
     if (flavour == NSX_STATIONARY && type == 0) {  // NSSolverStationary.hpp:132-153
       Control cu(100001, 1e-1 * vec_norm(c, su, nu));

@@ -71,6 +71,7 @@ void schur_symbolic(Ctx &c) {
   S.h_rowptr.assign(n + 1, 0);
   for (int64_t i = 0; i < n; ++i) S.h_rowptr[i + 1] = S.h_rowptr[i] + (int64_t)rows[i].size();
   S.nnz = S.h_rowptr[n];
+  S.nrb = S.ndesc = 0;
   S.h_col.resize(S.nnz);
   std::vector<int32_t> diag(n, -1);
   S.max_row = 0;
@@ -80,11 +81,12 @@ void schur_symbolic(Ctx &c) {
     auto it = std::lower_bound(rows[i].begin(), rows[i].end(), (int32_t)i);
     if (it != rows[i].end() && *it == i) diag[i] = (int32_t)(it - rows[i].begin());
   }
-  S.rowptr.upload(S.h_rowptr, c.stream);
-  S.col.upload(S.h_col, c.stream);
+  S.rowptr.alloc_padded(S.h_rowptr.size(), 4);
+  NSX_CUDA(cudaMemcpyAsync(S.rowptr.p, S.h_rowptr.data(), S.h_rowptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
+  S.col.alloc_padded(S.nnz, 8);
+  NSX_CUDA(cudaMemcpyAsync(S.col.p, S.h_col.data(), S.nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
   S.diag.upload(diag, c.stream);
-  S.val.alloc(S.nnz);
-  S.val.zero(c.stream);
+  S.val.alloc_padded(S.nnz, 8);
   c.Dvec.alloc(c.n_u);
   c.Dinv.alloc(c.n_u);
   NSX_CUDA(cudaStreamSynchronize(c.stream));

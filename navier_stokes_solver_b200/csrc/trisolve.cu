@@ -123,6 +123,92 @@ __global__ void __launch_bounds__(CHAIN_T) k_ilu_chain(TriArgs A, const int32_t 
   }
 }
 
+// ---- cooperative sweep: all levels of both sweeps in one launch, grid barrier between levels ----
+// With ~17 k rows per colour and ~17 k sub-warps in the grid a sub-warp owns about one row per
+// level, and a level costs one barrier plus the dependent chain rowptr -> (val, col) -> w[col].
+// Only the last link depends on the previous level, so the sub-warp loads the matrix entries of
+// its NEXT row into registers before it enters the barrier; after the barrier only the gather of
+// the work vector and the shuffle reduction remain.
+constexpr int PF = 4;  // prefetched entries per lane (rows of up to PF * TG entries per triangle are fully covered)
+struct RowPre {
+  int32_t row;
+  int32_t c[PF];
+  double v[PF];
+  int64_t rest_b, rest_e;
+  double dg, xin;
+};
+
+template <bool FWD>
+__device__ __forceinline__ void prefetch_row(const TriArgs &A, const int32_t *__restrict__ order, int64_t r, int64_t r1, int lane, RowPre &P) {
+  P.row = -1;
+  if (r >= r1) return;
+  const int32_t row = order[r];
+  P.row = row;
+  const int64_t b = A.rowptr[row], e = A.rowptr[row + 1], d = b + A.diag[row];
+  const int64_t lo = FWD ? b : d + 1, hi = FWD ? d : e;
+#pragma unroll
+  for (int t = 0; t < PF; ++t) {
+    const int64_t k = lo + lane + t * TG;
+    if (k < hi) { P.v[t] = __ldcg(A.val + k); P.c[t] = A.col[k]; }
+    else { P.v[t] = 0.0; P.c[t] = -1; }
+  }
+  P.rest_b = lo + PF * TG + lane; P.rest_e = hi;
+  P.dg = __ldcg(A.val + d);
+  P.xin = FWD ? A.x[A.perm[row]] : 0.0;
+}
+
+template <bool SGS, bool FWD>
+__device__ __forceinline__ void finish_row(const TriArgs &A, const RowPre &P, const cg::thread_block_tile<TG> &tile) {
+  if (P.row < 0) return;  // uniform over the tile
+  const double *src = FWD ? A.w : A.yp;
+  double s = 0;
+#pragma unroll
+  for (int t = 0; t < PF; ++t)
+    if (P.c[t] >= 0) s += P.v[t] * __ldcg(src + P.c[t]);
+  for (int64_t k = P.rest_b; k < P.rest_e; k += TG) s += __ldcg(A.val + k) * __ldcg(src + A.col[k]);
+#pragma unroll
+  for (int o = TG / 2; o > 0; o >>= 1) s += tile.shfl_down(s, o);
+  if (tile.thread_rank() == 0) {
+    if (FWD) {
+      const double r = P.xin - s;
+      A.w[P.row] = SGS ? r / P.dg : r;
+    } else {
+      const double wv = __ldcg(A.w + P.row);
+      const double r = SGS ? wv - s / P.dg : (wv - s) / P.dg;
+      A.yp[P.row] = r;
+      A.y[A.perm[P.row]] = r;
+    }
+  }
+}
+
+template <bool SGS>
+__global__ void __launch_bounds__(256) k_sweep_coop(TriArgs A, const int32_t *__restrict__ order_f, const int64_t *__restrict__ lvl_f, int nlf,
+                                                    const int32_t *__restrict__ order_b, const int64_t *__restrict__ lvl_b, int nlb) {
+  cg::grid_group grid = cg::this_grid();
+  auto tile = cg::tiled_partition<TG>(cg::this_thread_block());
+  const int lane = tile.thread_rank();
+  const int64_t sub = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / TG, nsub = (int64_t)gridDim.x * blockDim.x / TG;
+  RowPre P;
+  prefetch_row<true>(A, order_f, lvl_f[0] + sub, lvl_f[1], lane, P);
+  for (int l = 0; l < nlf; ++l) {
+    const int64_t r0 = lvl_f[l], r1 = lvl_f[l + 1];
+    finish_row<SGS, true>(A, P, tile);
+    for (int64_t r = r0 + sub + nsub; r < r1; r += nsub) tri_row<SGS, true>(A, order_f[r], tile);
+    if (l + 1 < nlf) prefetch_row<true>(A, order_f, r1 + sub, lvl_f[l + 2], lane, P);
+    else prefetch_row<false>(A, order_b, lvl_b[0] + sub, lvl_b[1], lane, P);
+    grid.sync();
+  }
+  for (int l = 0; l < nlb; ++l) {
+    const int64_t r0 = lvl_b[l], r1 = lvl_b[l + 1];
+    finish_row<SGS, false>(A, P, tile);
+    for (int64_t r = r0 + sub + nsub; r < r1; r += nsub) tri_row<SGS, false>(A, order_b[r], tile);
+    if (l + 1 < nlb) {
+      prefetch_row<false>(A, order_b, r1 + sub, lvl_b[l + 2], lane, P);
+      grid.sync();
+    }
+  }
+}
+
 __global__ void k_gather_values(int64_t nnz, const int64_t *__restrict__ src, const double *__restrict__ a, double *__restrict__ v) {
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) v[k] = a[src[k]];
 }
@@ -311,6 +397,22 @@ void ilu0_factor(Ctx &c, TriPlan &P, const DevCSR &A) {
 template <bool SGS>
 static void sweep(Ctx &c, TriPlan &P, double *y, const double *x) {
   TriArgs T = args_of(P, x, y);
+  const int nlf = (int)P.lvl_f.size() - 1, nlb = (int)P.lvl_b.size() - 1;
+  if (c.coop_sweep && nlf + nlb <= 512) {
+    if (!P.coop_grid) {
+      int per_sm = 0;
+      NSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_coop<SGS>, 256, 0));
+      const int64_t widest = std::max<int64_t>(1, (P.n * TG / std::max(1, std::min(nlf, nlb)) + 255) / 256);  // blocks an average level can fill
+      P.coop_grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)per_sm * c.num_sms, widest));
+    }
+    const int32_t *of = P.order_fwd.p, *ob = P.order_bwd.p;
+    const int64_t *lf = P.d_lvl_f.p, *lb = P.d_lvl_b.p;
+    int a_nlf = nlf, a_nlb = nlb;
+    void *args[] = {&T, &of, &lf, &a_nlf, &ob, &lb, &a_nlb};
+    NSX_CUDA(cudaLaunchCooperativeKernel((const void *)k_sweep_coop<SGS>, dim3(P.coop_grid), dim3(256), args, 0, c.stream));
+    c.stat_launches++;
+    return;
+  }
   for (const TriStep &s : P.steps_f) {
     if (s.kind == 0) {
       const int64_t r0 = P.lvl_f[s.l0], r1 = P.lvl_f[s.l0 + 1];

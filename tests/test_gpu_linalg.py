@@ -106,3 +106,33 @@ def test_inner_preconditioners_by_definition(setup, ordering, block, kind):
             assert dev.stat("LEVELS_F" if block == N.BLOCK_F else "LEVELS_MP") < 200
     finally:
         dev.set_option(N.OPT_ORDERING, 0)
+
+
+def test_spmv_kernel_variants_agree(setup):
+    """streaming (shared-memory staged) and sub-warp-per-row SpMV: same products up to summation order"""
+    d, orc, dev = setup
+    x = np.random.default_rng(8).uniform(-1, 1, d.n)
+    ref = orc.spmv(N.BLOCK_J, x)
+    for flag in (0, 1, 2):
+        dev.set_option(N.OPT_STREAM_SPMV, flag)
+        assert rel(dev.spmv(N.BLOCK_J, x), ref) < 1e-13
+        assert rel(dev.spmv(N.BLOCK_F, x[: d.n_u]), orc.spmv(N.BLOCK_F, x[: d.n_u])) < 1e-13
+        assert rel(dev.spmv(N.BLOCK_B, x[: d.n_u]), orc.spmv(N.BLOCK_B, x[: d.n_u])) < 1e-13
+        assert rel(dev.spmv(N.BLOCK_MP, x[d.n_u:]), orc.spmv(N.BLOCK_MP, x[d.n_u:])) < 1e-13
+    dev.set_option(N.OPT_STREAM_SPMV, 2)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_cooperative_sweep_equals_level_launches(setup, kind):
+    """multicolour sweeps: one cooperative launch with grid barriers == one launch per colour, bit for bit"""
+    d, orc, dev = setup
+    x = np.random.default_rng(9).uniform(-1, 1, d.n_u)
+    dev.set_option(N.OPT_ORDERING, 1)
+    try:
+        dev.set_option(N.OPT_COOP_SWEEP, 0)
+        y0 = dev.inner_apply(N.BLOCK_F, kind, x)
+        dev.set_option(N.OPT_COOP_SWEEP, 1)
+        y1 = dev.inner_apply(N.BLOCK_F, kind, x)
+        np.testing.assert_array_equal(y0, y1)
+    finally:
+        dev.set_option(N.OPT_ORDERING, 0)

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 def make(elem, mode, nu, nranks=1):
     d = N.Disc.generate(20, 8, nranks=nranks) if elem == "quad" else N.Disc.generate(16, 7, triangles=True, nranks=nranks)
-    orc, dev = N.Oracle(d), N.Device(d, ordering=0)
+    orc, dev = N.Oracle(d), N.Device(d, ordering=0, ortho=0)   # Ifpack's order, deal.II's modified Gram-Schmidt
     sol = N.synthetic_state(d, 99, noise=1e-4)
     for o in (orc,):
         o.vec(0)[:] = sol
@@ -56,7 +56,8 @@ def test_solve_matches_oracle(flavour, solver, prec, mode, elem):
     assert rc_o == 0 and rc_d == 0
     x_o, x_d = orc.vec(2), dev.download(N.VEC_DELTA)
     assert np.linalg.norm(x_d - x_o) <= 1e-8 * np.linalg.norm(x_o)
-    assert abs(it_d - it_o) <= max(3, 0.1 * it_o)   # rounding flips inner stopping tests now and then
+    # rounding flips inner stopping tests now and then; BiCGStab's count is erratic by nature
+    assert abs(it_d - it_o) <= max(3, (0.3 if solver == 2 else 0.1) * it_o)
     # and the answer solves the system: || J x - r || <= tol-ish
     J = orc.jacobian()
     assert np.linalg.norm(J @ x_d - orc.vec(3)) <= 50 * tol
@@ -92,3 +93,17 @@ def test_multicolour_order_converges_to_the_same_answer():
     print("natural (oracle)", it_o, "multicolour (gpu)", it_d)
     assert rc_d == 0
     assert np.linalg.norm(dev.download(N.VEC_DELTA) - orc.vec(2)) <= 1e-7 * np.linalg.norm(orc.vec(2))
+
+
+@pytest.mark.parametrize("solver", [0, 1])
+def test_batched_gram_schmidt_matches_modified(solver):
+    """The default orthogonalisation (two passes of batched classical Gram-Schmidt) against the
+    modified Gram-Schmidt chain of deal.II: same answer, iteration counts within a few percent."""
+    d, orc, dev = make("quad", N.MODE_NEWTON, 1 / 10.0)
+    rc_o, it_o, _, _ = orc.solve(N.STATIONARY, solver, 2, 1e-12, 2000)
+    dev.set_option(N.OPT_ORTHO, 1)
+    rc_d, it_d, _ = dev.solve(N.STATIONARY, solver, 2, 1e-12, 2000)
+    print("MGS (oracle)", it_o, "CGS2 (gpu)", it_d)
+    assert rc_o == 0 and rc_d == 0
+    assert abs(it_d - it_o) <= max(3, 0.1 * it_o)
+    assert np.linalg.norm(dev.download(N.VEC_DELTA) - orc.vec(2)) <= 1e-8 * np.linalg.norm(orc.vec(2))

@@ -1,0 +1,283 @@
+"""The CPU oracle (oracle/, a restatement of the reference's assembly + Krylov path) against checks
+that do not depend on it: structural identities of the assembled operators, manufactured fields,
+scipy's direct solver and sparse products, and dense restatements of ILU(0) / SGS.
+
+The reference holds no golden vector for this path: parity is UNPINNED at the
+deal.II / Trilinos boundary and these identities are what anchors the oracle instead."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import nsxlib as N
+
+
+@pytest.fixture(scope="module", params=["quad", "tri"])
+def prob(request):
+    d = N.Disc.generate(16, 8) if request.param == "quad" else N.Disc.generate(12, 6, triangles=True)
+    return d, N.Oracle(d)
+
+
+def support_points(d):
+    """support point of every dof from the cell tables (vertices + GLL / midpoint line nodes + interior)"""
+    cd = d.array("CELL_DOFS").reshape(d.ncells, d.dofs_per_cell).astype(np.int64)
+    cv = d.array("CELL_VERTICES").reshape(d.ncells, d.nvpc, 2)
+    X = np.zeros((d.n, 2))
+    g = [(1 - 1 / np.sqrt(5)) / 2, (1 + 1 / np.sqrt(5)) / 2]
+    if d.elem == 0:
+        ref_v = [(0, 0), (1, 0), (0, 1), (1, 1)] + [(0, g[0]), (0, g[1]), (1, g[0]), (1, g[1]), (g[0], 0), (g[1], 0), (g[0], 1), (g[1], 1)] + \
+                [(g[0], g[0]), (g[1], g[0]), (g[0], g[1]), (g[1], g[1])]
+        ref_p = [(0, 0), (1, 0), (0, 1), (1, 1), (0, .5), (1, .5), (.5, 0), (.5, 1), (.5, .5)]
+        comp = [0, 1, 2] * 4 + [0, 0, 1, 1, 2] * 4 + [0] * 4 + [1] * 4 + [2]
+        node = sum([[v, v, v] for v in range(4)], []) + sum([[4 + 2 * l, 5 + 2 * l, 4 + 2 * l, 5 + 2 * l, 4 + l] for l in range(4)], []) + \
+            [12, 13, 14, 15] * 2 + [8]
+        for i in range(41):
+            x, y = (ref_p if comp[i] == 2 else ref_v)[node[i]]
+            X[cd[:, i], 0] = cv[:, 0, 0] + x * (cv[:, 1, 0] - cv[:, 0, 0])
+            X[cd[:, i], 1] = cv[:, 0, 1] + y * (cv[:, 2, 1] - cv[:, 0, 1])
+    else:
+        for v in range(3):
+            for c in range(3):
+                X[cd[:, 3 * v + c]] = cv[:, v]
+        for l in range(3):
+            mid = 0.5 * (cv[:, l] + cv[:, (l + 1) % 3])
+            X[cd[:, 9 + 2 * l]] = mid
+            X[cd[:, 10 + 2 * l]] = mid
+    comp_of = np.zeros(d.n, int)
+    tab = np.frombuffer(d.array("FE_TABLES").tobytes()[32:32 + 4 * 41], dtype=np.int32)
+    for i in range(d.dofs_per_cell):
+        comp_of[cd[:, i]] = tab[i]
+    return X, comp_of
+
+
+def test_stokes_branch_structure(prob):
+    d, o = prob
+    o.vec(0)[:] = 0
+    o.assemble_cells(N.MODE_STOKES, 0.25)
+    F, Bt, B, Mp = o.csr(N.BLOCK_F), o.csr(N.BLOCK_BT), o.csr(N.BLOCK_B), o.csr(N.BLOCK_MP)
+    assert abs(F - F.T).max() < 1e-13 * abs(F).max()
+    assert abs(B - Bt.T).max() < 1e-14
+    assert abs(Mp - Mp.T).max() < 1e-15
+    # nu * stiffness: constants are in the kernel, F is positive semi-definite
+    X, comp = support_points(d)
+    ones_x = (comp[: d.n_u] == 0).astype(float)
+    assert np.abs(F @ ones_x).max() < 1e-12
+    z = np.random.default_rng(0).normal(size=d.n_u)
+    assert z @ (F @ z) > 0
+    # u_x - u_y couplings are in the pattern but numerically zero in the Stokes branch
+    Fc = F.tocoo()
+    cross = comp[Fc.row] != comp[Fc.col]
+    assert cross.any() and (Fc.data[cross] == 0).all()
+    # pressure mass: 1^T Mp 1 = area / nu
+    cv = d.array("CELL_VERTICES").reshape(d.ncells, d.nvpc, 2)
+    if d.elem == 0:
+        area = np.sum((cv[:, 1, 0] - cv[:, 0, 0]) * (cv[:, 2, 1] - cv[:, 0, 1]))
+    else:
+        a, b, c = cv[:, 0], cv[:, 1], cv[:, 2]
+        area = 0.5 * np.abs((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0])).sum()
+    assert abs(Mp.sum() * 0.25 - area) < 1e-13
+
+
+def test_divergence_of_a_linear_field(prob):
+    """B applied to the interpolant of u = (a x + b y, c x + e y) gives -(a + e) * int psi_m (Stokes sign)."""
+    d, o = prob
+    o.vec(0)[:] = 0
+    o.assemble_cells(N.MODE_STOKES, 1.0)
+    X, comp = support_points(d)
+    a, b, c, e = 0.3, -0.7, 1.1, 0.45
+    u = np.where(comp[: d.n_u] == 0, a * X[: d.n_u, 0] + b * X[: d.n_u, 1], c * X[: d.n_u, 0] + e * X[: d.n_u, 1])
+    lhs = o.csr(N.BLOCK_B) @ u
+    rhs = -(a + e) * np.asarray(o.csr(N.BLOCK_MP).sum(axis=1)).ravel()   # nu = 1: row sums = int psi_m
+    np.testing.assert_allclose(lhs, rhs, atol=1e-13)
+
+
+def test_newton_residual_is_consistent_with_the_jacobian(prob):
+    """r(u) assembled in the Newton branch and J(u): a finite difference of -r along a direction matches
+    J's action up to the reference's continuity-row sign (block (1,0) carries
+    '+', so the pressure rows of the difference quotient have the opposite sign)."""
+    d, o = prob
+    rng = np.random.default_rng(5)
+    X, comp = support_points(d)
+    u0 = np.zeros(d.n)
+    u0[: d.n_u] = np.where(comp[: d.n_u] == 0, 0.3 * X[: d.n_u, 1] * (0.41 - X[: d.n_u, 1]), 0.02 * np.sin(3 * X[: d.n_u, 0]))
+    u0[d.n_u:] = 0.5 - 0.1 * X[d.n_u:, 0]
+    w = rng.normal(size=d.n) * 1e-2
+    nu = 0.05
+
+    def res(u):
+        o.vec(0)[:] = u
+        o.assemble_cells(N.MODE_NEWTON, nu, p_out=0.0)
+        return o.vec(3).copy()
+    r0 = res(u0)
+    J = o.jacobian()
+    eps = 1e-6
+    fd = -(res(u0 + eps * w) - res(u0 - eps * w)) / (2 * eps)
+    Jw = J @ w
+    np.testing.assert_allclose(fd[: d.n_u], Jw[: d.n_u], atol=2e-7 * np.abs(Jw).max())
+    np.testing.assert_allclose(fd[d.n_u:], -Jw[d.n_u:], atol=2e-7 * np.abs(Jw).max())
+    assert np.abs(r0).max() > 0
+
+
+def test_unsteady_terms(prob):
+    d, o = prob
+    rng = np.random.default_rng(6)
+    sol = N.synthetic_state(d, 2, noise=1e-3)
+    old = sol + rng.normal(size=d.n) * 1e-3
+    o.vec(0)[:] = sol; o.vec(1)[:] = old
+    nu, dt = 0.02, 0.05
+    o.assemble_cells(N.MODE_UNSTEADY_NEWTON, nu, dt)
+    Fu, ru = o.csr(N.BLOCK_F), o.vec(3).copy()
+    o.assemble_cells(N.MODE_NEWTON, nu)
+    Fs, rs = o.csr(N.BLOCK_F), o.vec(3).copy()
+    M = (Fu - Fs) * dt            # velocity mass matrix
+    assert abs(M - M.T).max() < 1e-12 * abs(M).max()
+    du = (sol - old)[: d.n_u]
+    np.testing.assert_allclose(ru[: d.n_u] - rs[: d.n_u], -(M @ du) / dt, atol=1e-12)
+    np.testing.assert_allclose(ru[d.n_u:], rs[d.n_u:], atol=1e-15)
+    # first-iteration branch with solution_old == solution is the Stokes operator
+    o.vec(1)[:] = sol
+    o.assemble_cells(N.MODE_UNSTEADY_FIRST, nu, dt)
+    A = o.jacobian()
+    o.assemble_cells(N.MODE_STOKES, nu)
+    assert abs(A - o.jacobian()).max() < 1e-15
+
+
+def test_apply_boundary_values_semantics(prob):
+    d, o = prob
+    o.vec(0)[:] = N.synthetic_state(d, 3)
+    o.vec(2)[:] = 7.0
+    o.assemble(N.MODE_NEWTON, True, 0.1)
+    F, Bt = o.csr(N.BLOCK_F), o.csr(N.BLOCK_BT)
+    bc = d.array("BC_DOF").astype(np.int64)
+    v = d.inlet_values(0.1)
+    Fr = F[bc]
+    diag = F.diagonal()[bc]
+    assert (diag != 0).all()
+    off = Fr.copy(); off = off - sp.csr_matrix((diag, (np.arange(len(bc)), bc)), shape=Fr.shape)
+    assert abs(off).max() == 0 and abs(Bt[bc]).max() == 0
+    np.testing.assert_array_equal(o.vec(2)[bc], v)                    # delta = boundary value (warm start)
+    np.testing.assert_allclose(o.vec(3)[bc], v * diag, rtol=0, atol=0)  # rhs = value * diagonal
+    free = np.setdiff1d(np.arange(d.n), bc)
+    assert (o.vec(2)[free] == 7.0).all()
+    # columns are NOT eliminated (eliminate_columns = false): some free row still couples to a constrained dof
+    free_u = free[free < d.n_u]
+    assert abs(F[free_u][:, bc]).max() > 0
+
+
+@pytest.mark.parametrize("flavour,solver,prec,mode", [
+    (0, 1, 0, N.MODE_STOKES), (0, 0, 0, N.MODE_NEWTON), (0, 1, 2, N.MODE_NEWTON),
+    (1, 1, 0, N.MODE_UNSTEADY_NEWTON), (1, 1, 1, N.MODE_UNSTEADY_NEWTON), (1, 2, 2, N.MODE_UNSTEADY_NEWTON),
+    (1, 0, 2, N.MODE_UNSTEADY_NEWTON)])
+def test_solve_system_against_a_direct_solve(prob, flavour, solver, prec, mode):
+    d, o = prob
+    sol = N.synthetic_state(d, 4, noise=1e-4)
+    o.vec(0)[:] = sol; o.vec(1)[:] = sol; o.vec(2)[:] = 0
+    o.assemble(mode, True, 0.1, 0.01)
+    J, r = o.jacobian().tocsc(), o.vec(3).copy()
+    ref = spla.spsolve(J, r)
+    rc, it, fr, inner = o.solve(flavour, solver, prec, 1e-12, 5000)
+    assert rc == 0 and it > 0
+    assert np.linalg.norm(J @ o.vec(2) - r) < 1e-10
+    assert np.linalg.norm(o.vec(2) - ref) <= 1e-8 * np.linalg.norm(ref)
+    # warm start: a second call on the converged increment takes no iteration
+    rc, it2, _, _ = o.solve(flavour, solver, prec, 1e-9, 5000)
+    assert rc == 0 and it2 == 0
+
+
+def test_solver_error_paths(prob):
+    d, o = prob
+    o.vec(0)[:] = 0; o.vec(2)[:] = 0
+    o.assemble(N.MODE_STOKES, True, 0.1)
+    rc, it, fr, _ = o.solve(0, 1, 2, 1e-30, 4)
+    assert rc == 1 and it == 4                      # SolverControl::NoConvergence
+    assert o.solve(0, 1, 9, 1e-6, 10)[0] == 2       # std::invalid_argument
+    rc, it, _, _ = o.solve(0, 7, 2, 1e-6, 10)       # unknown solver: nothing solved, last_step() = 0
+    assert rc == 0 and it == 0
+
+
+def test_inner_preconditioners_by_definition(prob):
+    d, o = prob
+    o.vec(0)[:] = N.synthetic_state(d, 8)
+    o.assemble(N.MODE_NEWTON, False, 0.05)
+    for blk in (N.BLOCK_F, N.BLOCK_MP):
+        A = o.csr(blk).toarray()
+        n = A.shape[0]
+        x = np.random.default_rng(1).normal(size=n)
+        D, L, U = np.diag(np.diag(A)), np.tril(A, -1), np.triu(A, 1)
+        sgs = np.linalg.solve(D + U, D @ np.linalg.solve(D + L, x))
+        np.testing.assert_allclose(o.inner_apply(blk, 0, x), sgs, rtol=1e-9, atol=1e-12 * np.abs(sgs).max())
+        pat = o.csr(blk).copy(); pat.data[:] = 1; pat = pat.toarray() != 0
+        LU = A.copy()
+        for i in range(n):
+            for k in np.nonzero(pat[i, :i])[0]:
+                LU[i, k] /= LU[k, k]
+                js = np.nonzero(pat[i, k + 1:] & pat[k, k + 1:])[0] + k + 1
+                LU[i, js] -= LU[i, k] * LU[k, js]
+        lu = sp.csr_matrix((o.ilu0_factor(blk), o.csr(blk).indices, o.csr(blk).indptr), shape=A.shape).toarray()
+        np.testing.assert_allclose(lu[pat], LU[pat], rtol=1e-9, atol=1e-13 * np.abs(LU).max())
+        y = np.linalg.solve(np.triu(LU), np.linalg.solve(np.tril(LU, -1) + np.eye(n), x))
+        np.testing.assert_allclose(o.inner_apply(blk, 1, x), y, rtol=1e-8, atol=1e-11 * np.abs(y).max())
+
+
+def test_schur_complement_product(prob):
+    d, o = prob
+    o.vec(0)[:] = N.synthetic_state(d, 9)
+    o.assemble(N.MODE_NEWTON, False, 0.05)
+    S = o.schur()
+    F = o.csr(N.BLOCK_F)
+    ref = (o.csr(N.BLOCK_B) @ sp.diags(1.0 / F.diagonal()) @ o.csr(N.BLOCK_BT)).tocsr()
+    assert abs(S - ref).max() <= 1e-13 * abs(ref).max()
+    assert S.nnz >= ref.nnz     # the structural pattern (zeros kept), as EpetraExt's product
+
+
+@pytest.mark.parametrize("tri", [False, True])
+def test_lift_drag_of_hydrostatic_pressure(tri):
+    """u = 0, p = const: the force on the closed cylinder boundary vanishes (divergence theorem) -- on the
+    generated meshes only when every hole face is tagged 10, so check drag/lift = -p * sum(n w) instead."""
+    d = N.Disc.generate(22, 9, triangles=True) if tri else N.Disc.generate(30, 12)
+    o = N.Oracle(d)
+    o.vec(0)[:] = 0
+    o.vec(0)[d.n_u:] = 2.5
+    drag, lift = o.lift_drag(0.1)
+    cv = d.array("CELL_VERTICES").reshape(d.ncells, d.nvpc, 2)
+    fx = fy = 0.0
+    fv = [(0, 2, 1), (1, 3, 0), (0, 1, 2), (2, 3, 0)] if d.elem == 0 else [(0, 1, 2), (1, 2, 0), (2, 0, 1)]
+    for c, f in zip(d.array("CYL_CELL"), d.array("CYL_FACE")):
+        a, b, oo = fv[f]
+        t = cv[c, b] - cv[c, a]
+        n = np.array([t[1], -t[0]])
+        if n @ (cv[c, oo] - cv[c, a]) > 0:
+            n = -n
+        fx += 2.5 * n[0]; fy += 2.5 * n[1]      # -(-p I) n w summed over the face: |t| cancels the unit normal
+    assert abs(drag - fx) < 1e-13 and abs(lift - fy) < 1e-13
+    assert len(d.array("CYL_CELL")) > 0
+
+
+def test_stationary_driver_reproduces_the_reference_control_flow():
+    """solve_newton's quirks: the inlet is imposed once, the first Stokes pass is
+    accepted at alpha = 1, later Stokes iterations cannot reduce the (solution-independent) residual and
+    end on a zero-iteration solve or an exhausted line search."""
+    d = N.Disc.generate(12, 5)
+    o = N.Oracle(d)
+    rc, log, nu, u = o.newton_stationary(10.0, 1, 2, 1e-10, max_newton_total=3)
+    assert rc == 0 and nu == 0.1
+    kinds = log[:, 0].astype(int).tolist()
+    assert kinds[0] == 0 and kinds[1] == 1 and kinds[2] == 2          # stage, newton residual, solve
+    ls = log[log[:, 0] == 3]
+    assert ls[0, 1] == 1.0                                            # first trial alpha = 1 accepted
+    first_solve = log[log[:, 0] == 2][0]
+    assert first_solve[1] > 0
+    # Stokes mode: the residual norm after every assembly is the same number (outlet term + BC rows)
+    newton = log[log[:, 0] == 1]
+    assert newton.shape[0] >= 2
+    assert abs(newton[1, 2] - ls[0, 2]) < 1e-15
+
+
+def test_unsteady_driver_first_step():
+    d = N.Disc.generate(10, 4, triangles=True)
+    o = N.Oracle(d, inlet_amplitude=0.3)
+    rc, log, nu = o.run_unsteady(1.0, 0.02, 0.01, 1, 2, 1e-8, n_steps_max=1)
+    assert rc == 0 and nu == 1.0
+    coeffs = log[log[:, 0] == 6]
+    assert coeffs.shape[0] == 1 and np.isfinite(coeffs[0, 2:6]).all()
+    assert (log[:, 0] == 5).sum() == 1
