@@ -45,7 +45,8 @@ enum nsx_option {
 enum nsx_stat {
   NSX_STAT_INNER_F = 0, NSX_STAT_INNER_S = 1, NSX_STAT_PRECOND_APPLIES = 2, NSX_STAT_KERNEL_LAUNCHES = 3,
   NSX_STAT_LEVELS_F = 4, NSX_STAT_LEVELS_MP = 5, NSX_STAT_LEVELS_S = 6, NSX_STAT_SPMV_CALLS = 7,
-  NSX_STAT_ASSEMBLY_COLOURS = 8, NSX_STAT_ASSEMBLY_TABLES = 9, NSX_STAT_LAST_STEP = 10
+  NSX_STAT_ASSEMBLY_COLOURS = 8, NSX_STAT_ASSEMBLY_TABLES = 9, NSX_STAT_LAST_STEP = 10,
+  NSX_STAT_HALO_EXCHANGES = 11, NSX_STAT_ALLREDUCES = 12
 };
 
 /* ctor of the solver objects (NSSolverStationary.hpp:339-351): one context per rank / GPU.
@@ -73,12 +74,38 @@ int nsx_set_dirichlet(nsx_ctx *ctx, int64_t n, const uint32_t *dof, const double
 /* Owned ranges of the velocity / pressure blocks per rank (block_owned_dofs, NSSolverStationary.cpp:237-240):
  * the inner ILU / SGS / AMG are local to each range (Ifpack overlap 0). */
 int nsx_set_ranks(nsx_ctx *ctx, int nranks, const int64_t *owned_u, const int64_t *owned_p);
+/* ---- one rank of a row-partitioned run (mpirun -n N in the reference; one process per GPU here) ----
+ * The reference partitions the cells, and every rank owns one contiguous range of each block
+ * (locally_owned_dofs / block_owned_dofs, NSSolverStationary.cpp:226-242).  A rank hands this library its own
+ * share in LOCAL numbering: per block the owned dofs first, then the ghosts (locally relevant, not owned)
+ * grouped by owner.  nsx_set_discretisation then takes the local cells (own cells plus the ghost layer whose
+ * contributions reach owned rows), cell_dofs in local ids (pressure ids offset by the local velocity count)
+ * and n_u / n_p = owned + ghost counts; nsx_set_partition says how many of them are owned; nsx_set_pattern
+ * takes the OWNED rows of each block with local column ids; nsx_set_dirichlet / nsx_set_faces take local ids;
+ * block vectors passed to nsx_vec_upload / download hold the owned entries [velocity | pressure] only.
+ * Call order: create, set_discretisation, set_partition, set_halo x2, set_pattern x4, faces, dirichlet,
+ * comm_init, finalize_setup.  assemble / solve / lift_drag / halo_exchange are collective. */
+int nsx_set_partition(nsx_ctx *ctx, int64_t n_u_owned, int64_t n_p_owned);
+/* Ghost import plan of one block (0 velocity, 1 pressure) -- what Epetra_Import holds for the reference's
+ * ghosted vectors (NSSolverStationary.cpp:309-314): to neighbour i go the owned entries
+ * send_idx[send_ptr[i] .. send_ptr[i+1]); from it come the ghosts recv_ptr[i] .. recv_ptr[i+1) (0 = first ghost),
+ * in the same order on both sides. */
+int nsx_set_halo(nsx_ctx *ctx, int block, int n_neighbours, const int32_t *neighbour, const int64_t *send_ptr, const int32_t *send_idx,
+                 const int64_t *recv_ptr);
+/* NCCL bootstrap: rank 0 creates the 128-byte id, the launcher broadcasts it (MPI_Bcast, torch.distributed, a file),
+ * every rank then joins.  No-op for nranks == 1. */
+int nsx_comm_unique_id(void *id128);
+int nsx_comm_init(nsx_ctx *ctx, const void *id128);
+
 /* Builds the device-side gather maps; must follow the setters and precede assemble/solve. */
 int nsx_finalize_setup(nsx_ctx *ctx);
 
 /* Block vectors [velocity | pressure] of length n_u + n_p (NSSolverStationary.hpp:451-463). */
 int nsx_vec_upload(nsx_ctx *ctx, int which, const double *host);
 int nsx_vec_download(nsx_ctx *ctx, int which, double *host);
+/* ghost import of one block vector, and a look at the imported values (tests) */
+int nsx_halo_exchange(nsx_ctx *ctx, int which);
+int nsx_vec_download_ghosts(nsx_ctx *ctx, int which, double *host_u_ghosts, double *host_p_ghosts);
 /* device-side `v = value` and `dst = src` (Trilinos `vector = 0.0`, `a = b`; NSSolverStationary.cpp:338-340, 715) */
 int nsx_vec_set(nsx_ctx *ctx, int which, double value);
 int nsx_vec_copy(nsx_ctx *ctx, int dst, int src);

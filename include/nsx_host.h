@@ -21,6 +21,13 @@ typedef struct nsx_disc nsx_disc;
 nsx_disc *nsx_disc_generate(int nx, int ny, int triangles, int nranks);
 /* Gmsh 2.2 mesh (reference: NSSolverStationary.cpp:146-176), P2/P1. */
 nsx_disc *nsx_disc_from_gmsh(const char *path, int nranks);
+/* One rank's share of a partitioned discretisation (what the locally_owned / locally_relevant index sets,
+ * the owned rows of the sparsity pattern and the Epetra import plans are in the reference,
+ * NSSolverStationary.cpp:226-305): the cells touching a dof of `rank` (own cells + one ghost layer), local dof
+ * numbering per block (owned first, then ghosts ascending by global id), owned-row patterns with local
+ * columns, ghost import plans, local boundary lists.  The result answers the same queries as a global
+ * nsx_disc; NSX_DI_N_U / N_P then count owned + ghost dofs. */
+nsx_disc *nsx_disc_local(const nsx_disc *global, int rank);
 void nsx_disc_free(nsx_disc *d);
 /* last error text of a failed nsx_disc_* call on this thread */
 const char *nsx_host_last_error(void);
@@ -36,7 +43,12 @@ enum nsx_disc_info_t {
   NSX_DI_NQF = 7,
   NSX_DI_NRANKS = 8,
   NSX_DI_NBC = 9,
-  NSX_DI_NVPC = 10
+  NSX_DI_NVPC = 10,
+  NSX_DI_IS_LOCAL = 11,   /* 1 for the result of nsx_disc_local */
+  NSX_DI_RANK = 12,
+  NSX_DI_JOB_RANKS = 13,  /* ranks of the partition a local view was cut from */
+  NSX_DI_N_U_OWNED = 14,
+  NSX_DI_N_P_OWNED = 15
 };
 int64_t nsx_disc_info(const nsx_disc *d, int what);
 
@@ -58,7 +70,13 @@ enum nsx_disc_array_t {
   NSX_DA_CYL_CELL = 32, NSX_DA_CYL_FACE = 33,            /* int32 */
   NSX_DA_BFACES = 34,        /* int32 [n * 3] (cell, face, boundary id) */
   NSX_DA_MATERIAL = 35,      /* int32 [ncells] */
-  NSX_DA_FE_TABLES = 40      /* the raw nsx::FETables struct (bytes) */
+  NSX_DA_FE_TABLES = 40,     /* the raw nsx::FETables struct (bytes) */
+  /* local views only */
+  NSX_DA_L2G_U = 50, NSX_DA_L2G_P = 51,      /* int64: local -> global id inside the block */
+  NSX_DA_CELL_GLOBAL = 52,                   /* int32: local cell -> global cell */
+  NSX_DA_CELL_OWNED = 53,                    /* uint8: the cell belongs to this rank's subdomain */
+  NSX_DA_HALO_U_NBR = 60, NSX_DA_HALO_U_SEND_PTR = 61, NSX_DA_HALO_U_SEND_IDX = 62, NSX_DA_HALO_U_RECV_PTR = 63,  /* int32 / int64 / int32 / int64 */
+  NSX_DA_HALO_P_NBR = 64, NSX_DA_HALO_P_SEND_PTR = 65, NSX_DA_HALO_P_SEND_IDX = 66, NSX_DA_HALO_P_RECV_PTR = 67
 };
 /* Returns a pointer into the discretisation (valid until nsx_disc_free) and the element count. */
 const void *nsx_disc_array(const nsx_disc *d, int what, int64_t *count);

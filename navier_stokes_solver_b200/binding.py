@@ -6,20 +6,24 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIBNSX = os.path.join(ROOT, "navier_stokes_solver_b200", "libnsx.so")
+LIBNSX = os.environ.get("NSX_LIB") or os.path.join(ROOT, "navier_stokes_solver_b200", "libnsx.so")
 
 c_i64p = C.POINTER(C.c_int64)
 c_dp = C.POINTER(C.c_double)
 
 # enum mirrors (include/nsx_host.h, include/nsx.h)
-DI = dict(ELEM=0, NCELLS=1, NVERTS=2, N_U=3, N_P=4, DOFS_PER_CELL=5, NQ=6, NQF=7, NRANKS=8, NBC=9, NVPC=10)
+DI = dict(ELEM=0, NCELLS=1, NVERTS=2, N_U=3, N_P=4, DOFS_PER_CELL=5, NQ=6, NQF=7, NRANKS=8, NBC=9, NVPC=10,
+          IS_LOCAL=11, RANK=12, JOB_RANKS=13, N_U_OWNED=14, N_P_OWNED=15)
 DA = dict(CELL_DOFS=(0, np.uint32), CELL_VERTICES=(1, np.float64), CELL_RANK=(2, np.int32),
           OWNED_U=(3, np.int64), OWNED_P=(4, np.int64),
           F_ROWPTR=(10, np.int64), F_COL=(11, np.int32), BT_ROWPTR=(12, np.int64), BT_COL=(13, np.int32),
           B_ROWPTR=(14, np.int64), B_COL=(15, np.int32), MP_ROWPTR=(16, np.int64), MP_COL=(17, np.int32),
           BC_DOF=(20, np.uint32), BC_SHAPE=(21, np.float64), BC_ON_INLET=(22, np.uint8), BC_Y=(23, np.float64),
           OUTLET_CELL=(30, np.int32), OUTLET_FACE=(31, np.int32), CYL_CELL=(32, np.int32), CYL_FACE=(33, np.int32),
-          BFACES=(34, np.int32), MATERIAL=(35, np.int32), FE_TABLES=(40, np.uint8))
+          BFACES=(34, np.int32), MATERIAL=(35, np.int32), FE_TABLES=(40, np.uint8),
+          L2G_U=(50, np.int64), L2G_P=(51, np.int64), CELL_GLOBAL=(52, np.int32), CELL_OWNED=(53, np.uint8),
+          HALO_U_NBR=(60, np.int32), HALO_U_SEND_PTR=(61, np.int64), HALO_U_SEND_IDX=(62, np.int32), HALO_U_RECV_PTR=(63, np.int64),
+          HALO_P_NBR=(64, np.int32), HALO_P_SEND_PTR=(65, np.int64), HALO_P_SEND_IDX=(66, np.int32), HALO_P_RECV_PTR=(67, np.int64))
 BLOCK_F, BLOCK_BT, BLOCK_B, BLOCK_MP, BLOCK_S, BLOCK_J = 0, 1, 2, 3, 4, 5
 MODE_STOKES, MODE_NEWTON, MODE_UNSTEADY_FIRST, MODE_UNSTEADY_NEWTON = 0, 1, 2, 3
 VEC_SOLUTION, VEC_SOLUTION_OLD, VEC_DELTA, VEC_RESIDUAL, VEC_EVAL, VEC_TMP0, VEC_TMP1 = 0, 1, 2, 3, 4, 5, 6
@@ -27,7 +31,7 @@ STATIONARY, UNSTEADY = 0, 1
 NSX_OK, NSX_E_NOCONV, NSX_E_BADARG, NSX_E_CUDA, NSX_E_COMM, NSX_E_STATE = 0, 1, 2, 3, 4, 5
 OPT_ORDERING, OPT_VERBOSE, OPT_ORTHO, OPT_COOP_SWEEP, OPT_STREAM_SPMV = 0, 1, 2, 3, 4
 STAT = dict(INNER_F=0, INNER_S=1, PRECOND_APPLIES=2, KERNEL_LAUNCHES=3, LEVELS_F=4, LEVELS_MP=5, LEVELS_S=6,
-            SPMV_CALLS=7, ASSEMBLY_COLOURS=8, ASSEMBLY_TABLES=9, LAST_STEP=10)
+            SPMV_CALLS=7, ASSEMBLY_COLOURS=8, ASSEMBLY_TABLES=9, LAST_STEP=10, HALO_EXCHANGES=11, ALLREDUCES=12)
 # every entry point include/nsx.h declares (tests check that the library exports each one)
 NSX_SYMBOLS = ["nsx_create", "nsx_destroy", "nsx_last_error", "nsx_set_option", "nsx_get_stat", "nsx_set_discretisation",
                "nsx_set_pattern", "nsx_set_faces", "nsx_set_dirichlet", "nsx_set_ranks", "nsx_finalize_setup",
@@ -35,7 +39,10 @@ NSX_SYMBOLS = ["nsx_create", "nsx_destroy", "nsx_last_error", "nsx_set_option", 
                "nsx_copy_old", "nsx_lift_drag", "nsx_assemble_cells", "nsx_get_block_nnz", "nsx_get_block_pattern",
                "nsx_get_block_values", "nsx_set_block_values", "nsx_spmv", "nsx_inner_apply", "nsx_ilu0_factor",
                "nsx_schur", "nsx_precond_apply", "nsx_set_time_params", "nsx_time_kernel", "nsx_synchronize",
-               "nsx_get_ordering"]
+               "nsx_get_ordering", "nsx_set_partition", "nsx_set_halo", "nsx_comm_unique_id", "nsx_comm_init",
+               "nsx_halo_exchange", "nsx_vec_download_ghosts"]
+NSX_HOST_SYMBOLS = ["nsx_disc_generate", "nsx_disc_from_gmsh", "nsx_disc_local", "nsx_disc_free", "nsx_host_last_error", "nsx_disc_info",
+                    "nsx_disc_array", "nsx_disc_inlet_values"]
 
 _nsx = None
 
@@ -52,6 +59,8 @@ def nsx():
         L.nsx_disc_from_gmsh.restype = C.c_void_p
         L.nsx_disc_from_gmsh.argtypes = [C.c_char_p, C.c_int]
         L.nsx_disc_free.argtypes = [C.c_void_p]
+        L.nsx_disc_local.restype = C.c_void_p
+        L.nsx_disc_local.argtypes = [C.c_void_p, C.c_int]
         L.nsx_disc_info.restype = C.c_int64
         L.nsx_disc_info.argtypes = [C.c_void_p, C.c_int]
         L.nsx_disc_array.restype = C.c_void_p
@@ -96,6 +105,12 @@ def nsx():
         L.nsx_time_kernel.argtypes = [vp, i32, i32, i32, c_dp]
         L.nsx_synchronize.argtypes = [vp]
         L.nsx_get_ordering.argtypes = [vp, i32, vp]
+        L.nsx_set_partition.argtypes = [vp, i64, i64]
+        L.nsx_set_halo.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+        L.nsx_comm_unique_id.argtypes = [vp]
+        L.nsx_comm_init.argtypes = [vp, vp]
+        L.nsx_halo_exchange.argtypes = [vp, i32]
+        L.nsx_vec_download_ghosts.argtypes = [vp, i32, vp, vp]
         _nsx = L
     return _nsx
 
@@ -115,6 +130,27 @@ class Disc:
         for k, v in DI.items():
             setattr(self, k.lower(), int(L.nsx_disc_info(self.h, v)))
         self.n = self.n_u + self.n_p
+        self.n_owned = self.n_u_owned + self.n_p_owned
+
+    def local(self, rank):
+        """This rank's share (own cells + ghost layer, local numbering, owned-row patterns, halo plans)."""
+        return Disc(nsx().nsx_disc_local(self.h, rank))
+
+    def owned_global_ids(self):
+        """Global block-vector positions [velocity | pressure] of a local view's owned entries (n_u_global needed
+        for the pressure offset is passed by the caller through gather/scatter helpers below)."""
+        return self.array("L2G_U")[: self.n_u_owned], self.array("L2G_P")[: self.n_p_owned]
+
+    def scatter_owned(self, global_vec, n_u_global):
+        """Owned entries [u | p] of this rank taken from a global block vector."""
+        gu, gp = self.owned_global_ids()
+        return np.concatenate([global_vec[gu], global_vec[n_u_global + gp]])
+
+    def gather_owned(self, local_vec, global_vec, n_u_global):
+        """Writes this rank's owned entries into a global block vector."""
+        gu, gp = self.owned_global_ids()
+        global_vec[gu] = local_vec[: self.n_u_owned]
+        global_vec[n_u_global + gp] = local_vec[self.n_u_owned:]
 
     @classmethod
     def generate(cls, nx, ny, triangles=False, nranks=1):
@@ -181,12 +217,17 @@ class Device:
     """One GPU context of the hot path (include/nsx.h) filled from a Disc.  Every method is a thin call
     through the C ABI; there is no CPU fallback (construction fails without a CUDA device)."""
 
-    def __init__(self, disc, device_id=0, inlet_amplitude=0.1, ordering=None, stream=None, ortho=None):
+    def __init__(self, disc, device_id=0, inlet_amplitude=0.1, ordering=None, stream=None, ortho=None, comm_id=None):
+        """disc: a global Disc (one GPU) or a local view (Disc.local(rank)) of a partitioned run; for the
+        latter comm_id is the 128-byte NCCL id shared by all ranks (Device.new_comm_id() on rank 0)."""
         L = nsx()
         self.disc = disc
-        self.n_u, self.n_p, self.n = disc.n_u, disc.n_p, disc.n
+        local = bool(disc.is_local)
+        # sizes of the block vectors this context exchanges with the host: the owned entries
+        self.n_u, self.n_p = (disc.n_u_owned, disc.n_p_owned) if local else (disc.n_u, disc.n_p)
+        self.n = self.n_u + self.n_p
         h = C.c_void_p()
-        rc = L.nsx_create(0, 1, device_id, stream, C.byref(h))
+        rc = L.nsx_create(disc.rank if local else 0, disc.job_ranks if local else 1, device_id, stream, C.byref(h))
         if rc:
             raise NsxError(rc, "nsx_create failed (no CUDA device? the product has no CPU path)")
         self.h = h
@@ -197,8 +238,13 @@ class Device:
         cd = np.ascontiguousarray(disc.array("CELL_DOFS"))
         cv = np.ascontiguousarray(disc.array("CELL_VERTICES"))
         self._ck(L.nsx_set_discretisation(self.h, disc.elem, disc.ncells, ptr(cv), ptr(cd), disc.n_u, disc.n_p))
-        shapes = {BLOCK_F: (disc.n_u, disc.n_u), BLOCK_BT: (disc.n_u, disc.n_p),
-                  BLOCK_B: (disc.n_p, disc.n_u), BLOCK_MP: (disc.n_p, disc.n_p)}
+        if local:
+            self._ck(L.nsx_set_partition(self.h, disc.n_u_owned, disc.n_p_owned))
+            for blk, nm in ((0, "U"), (1, "P")):
+                nbr, sp, si, rp = (np.ascontiguousarray(disc.array(f"HALO_{nm}_{k}")) for k in ("NBR", "SEND_PTR", "SEND_IDX", "RECV_PTR"))
+                self._ck(L.nsx_set_halo(self.h, blk, len(nbr), ptr(nbr), ptr(sp), ptr(si), ptr(rp)))
+        shapes = {BLOCK_F: (self.n_u, disc.n_u), BLOCK_BT: (self.n_u, disc.n_p),
+                  BLOCK_B: (self.n_p, disc.n_u), BLOCK_MP: (self.n_p, disc.n_p)}
         self.shapes = shapes
         for blk, name in ((BLOCK_F, "F"), (BLOCK_BT, "BT"), (BLOCK_B, "B"), (BLOCK_MP, "MP")):
             rp, col = disc.pattern(name)
@@ -210,13 +256,40 @@ class Device:
         bc_dof = disc.array("BC_DOF")
         bc_val = disc.inlet_values(inlet_amplitude)
         self._ck(L.nsx_set_dirichlet(self.h, len(bc_dof), ptr(bc_dof), ptr(bc_val)))
-        ou, op = disc.array("OWNED_U"), disc.array("OWNED_P")
-        self._ck(L.nsx_set_ranks(self.h, disc.nranks, ptr(ou), ptr(op)))
+        if local:
+            if disc.job_ranks > 1:
+                if comm_id is None:
+                    raise ValueError("a partitioned run needs the shared NCCL id (comm_id)")
+                buf = (C.c_char * 128).from_buffer_copy(bytes(comm_id))
+                self._ck(L.nsx_comm_init(self.h, buf))
+        else:
+            ou, op = disc.array("OWNED_U"), disc.array("OWNED_P")
+            self._ck(L.nsx_set_ranks(self.h, disc.nranks, ptr(ou), ptr(op)))
         self._ck(L.nsx_finalize_setup(self.h))
+
+    @staticmethod
+    def new_comm_id():
+        buf = (C.c_char * 128)()
+        rc = nsx().nsx_comm_unique_id(buf)
+        if rc:
+            raise NsxError(rc, "ncclGetUniqueId failed (is NCCL loadable?)")
+        return bytes(buf)
+
+    def halo_exchange(self, which):
+        self._ck(nsx().nsx_halo_exchange(self.h, which))
+
+    def download_ghosts(self, which):
+        gu = np.zeros(self.disc.n_u - self.n_u)
+        gp = np.zeros(self.disc.n_p - self.n_p)
+        self._ck(nsx().nsx_vec_download_ghosts(self.h, which, ptr(gu), ptr(gp)))
+        return gu, gp
 
     def _ck(self, rc):
         if rc:
             raise NsxError(rc, nsx().nsx_last_error(self.h).decode())
+
+    def last_error(self):
+        return nsx().nsx_last_error(self.h).decode()
 
     def set_option(self, opt, value):
         self._ck(nsx().nsx_set_option(self.h, opt, value))
@@ -300,7 +373,9 @@ class Device:
     def csr(self, block):
         import scipy.sparse as sp
         rp, col = self.pattern(block)
-        ncols = self.n_u if block in (BLOCK_F, BLOCK_B) else self.n_p
+        ncols = self.disc.n_u if block in (BLOCK_F, BLOCK_B) else self.disc.n_p   # owned + ghost columns on a partitioned system
+        if block == BLOCK_S:
+            ncols = self.n_p
         return sp.csr_matrix((self.values(block), col, rp), shape=(len(rp) - 1, ncols))
 
     def _block_vec(self, block, x, cols=True):

@@ -76,11 +76,12 @@ void build_assembly_maps(Ctx &c) {
   const uint32_t *cd = c.h_cell_dofs.data();
 
   // --- greedy colouring over the "shares a vertex" graph; the u_x dof of a vertex names it ---
-  std::vector<int64_t> vptr(c.n_u + 1, 0);
+  const int64_t lu = c.n_u + c.n_ug;   // local velocity dofs (owned + ghost): the pressure ids of the cell table start here
+  std::vector<int64_t> vptr(lu + 1, 0);
   for (int64_t k = 0; k < nc; ++k)
     for (int v = 0; v < nv; ++v) vptr[cd[k * nd + 3 * v] + 1]++;
-  for (int64_t i = 0; i < c.n_u; ++i) vptr[i + 1] += vptr[i];
-  std::vector<int32_t> vcell(vptr[c.n_u]);
+  for (int64_t i = 0; i < lu; ++i) vptr[i + 1] += vptr[i];
+  std::vector<int32_t> vcell(vptr[lu]);
   {
     std::vector<int64_t> fill(vptr.begin(), vptr.end() - 1);
     for (int64_t k = 0; k < nc; ++k)
@@ -129,12 +130,13 @@ void build_assembly_maps(Ctx &c) {
       try {
         for (int i = 0; i < nd; ++i) {
           const bool ip = T.dof_comp[i] == 2;
-          const int64_t ri = ip ? (int64_t)cd[k * nd + i] - c.n_u : cd[k * nd + i];
+          const int64_t ri = ip ? (int64_t)cd[k * nd + i] - lu : cd[k * nd + i];
+          const bool row_owned = ri < (ip ? c.n_p : c.n_u);   // ghost rows are assembled by their owner: offset 0 into the sink
           for (int j = 0; j < nd; ++j) {
             const bool jp = T.dof_comp[j] == 2;
-            const int32_t cj = (int32_t)(jp ? (int64_t)cd[k * nd + j] - c.n_u : cd[k * nd + j]);
+            const int32_t cj = (int32_t)(jp ? (int64_t)cd[k * nd + j] - lu : cd[k * nd + j]);
             const DevCSR &A = ip ? (jp ? c.Mp : c.B) : (jp ? c.Bt : c.F);
-            t[i * nd + j] = (uint16_t)find_in_row(A, ri, cj);
+            t[i * nd + j] = row_owned ? (uint16_t)find_in_row(A, ri, cj) : (uint16_t)0;
           }
         }
       } catch (const std::exception &e) {
@@ -182,10 +184,17 @@ void build_assembly_maps(Ctx &c) {
     }
     std::vector<uint32_t> dof;
     std::vector<double> val;
-    for (auto &kv : acc) { dof.push_back(kv.first); val.push_back(kv.second); }
+    for (auto &kv : acc)
+      if ((int64_t)kv.first < c.n_u) { dof.push_back(kv.first); val.push_back(kv.second); }  // owned rows only
     c.n_outlet = (int64_t)dof.size();
     c.outlet_dof.upload(dof, c.stream);
     c.outlet_unit.upload(val, c.stream);
+  }
+  {  // cell-table dof id -> position in a vector laid out [u owned | p owned | u ghosts | p ghosts]
+    std::vector<int32_t> vmap(lu + c.n_p + c.n_pg);
+    for (int64_t d = 0; d < lu; ++d) vmap[d] = (int32_t)(d < c.n_u ? d : d + c.n_p);
+    for (int64_t m = 0; m < c.n_p + c.n_pg; ++m) vmap[lu + m] = (int32_t)(m < c.n_p ? c.n_u + m : c.n_u + c.n_ug + m);
+    c.vmap.upload(vmap, c.stream);
   }
   c.cyl_cell.upload(c.h_cyl_cell, c.stream);
   c.cyl_face.upload(c.h_cyl_face, c.stream);
@@ -214,7 +223,9 @@ struct AsmArgs {
   const uint16_t *pat_off;
   const int32_t *cells;
   int ncells;
-  int64_t n_u;
+  int64_t n_u_loc, n_u_own, n_p_own;         // pressure ids of the cell table start at n_u_loc; rows >= n_*_own are ghosts
+  int64_t F_sink, Bt_sink, B_sink, Mp_sink;  // position in each value array that swallows the ghost rows' contributions
+  const int32_t *vmap;
   const FETables *fe;
 };
 
@@ -262,18 +273,22 @@ __global__ void __launch_bounds__(TPC *CPB) k_assemble(const AsmArgs A) {
     if (active) {
       for (int i = lt; i < ND; i += TPC) {
         const uint32_t d = A.cell_dofs[(int64_t)cell * ND + i];
-        sdof[slot][i] = d;
+        const uint32_t vi = (uint32_t)A.vmap[d];
+        sdof[slot][i] = vi;
         const int comp = T.dof_comp[i], node = T.dof_node[i];
-        const double s = A.sol[d];
+        const double s = A.sol[vi];
         if (comp == 2) {
+          const int64_t m = (int64_t)d - A.n_u_loc;
+          const bool own = m < A.n_p_own;
           sP[slot][node] = s;
-          srb0[slot][i] = A.B_rp[d - A.n_u];
-          srb1[slot][i] = A.Mp_rp[d - A.n_u];
+          srb0[slot][i] = own ? A.B_rp[m] : A.B_sink;
+          srb1[slot][i] = own ? A.Mp_rp[m] : A.Mp_sink;
         } else {
+          const bool own = (int64_t)d < A.n_u_own;
           sU[slot][node][comp] = s;
-          sUo[slot][node][comp] = unsteady ? A.sol_old[d] : 0.0;
-          srb0[slot][i] = A.F_rp[d];
-          srb1[slot][i] = A.Bt_rp[d];
+          sUo[slot][node][comp] = unsteady ? A.sol_old[vi] : 0.0;
+          srb0[slot][i] = own ? A.F_rp[d] : A.F_sink;
+          srb1[slot][i] = own ? A.Bt_rp[d] : A.Bt_sink;
         }
       }
       for (int i = lt; i < NVPC * 2; i += TPC) sxv[slot][i] = A.cell_vertices[(int64_t)cell * NVPC * 2 + i];
@@ -460,7 +475,7 @@ __global__ void k_apply_bc(int64_t nbc, const uint32_t *bc_dof, const double *bc
 
 // compute_lift_drag (NSSolverStationary.cpp:835-892): one thread per boundary-10 face
 __global__ void k_lift_drag(int64_t nfaces, const int32_t *fcell, const int32_t *fface, const FETables *fe, const double *cell_vertices,
-                            const uint32_t *cell_dofs, const double *sol, double nu, double *force) {
+                            const uint32_t *cell_dofs, const int32_t *vmap, const double *sol, double nu, double *force) {
   const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k >= nfaces) return;
   const FETables &T = *fe;
@@ -478,7 +493,7 @@ __global__ void k_lift_drag(int64_t nfaces, const int32_t *fcell, const int32_t 
     const double Ji[2][2] = {{J[1][1] / det, -J[0][1] / det}, {-J[1][0] / det, J[0][0] / det}};
     double g[2][2] = {{0, 0}, {0, 0}}, p = 0;
     for (int i = 0; i < nd; ++i) {
-      const double s = sol[dofs[i]];
+      const double s = sol[vmap[dofs[i]]];
       const int comp = T.dof_comp[i], node = T.dof_node[i];
       if (comp == 2) p += s * T.Npf[f][node][q];
       else {
@@ -509,7 +524,11 @@ void assemble_cells(Ctx &c, int mode, double nu, double dt, double p_out) {
   A.F_rp = c.F.rowptr.p; A.Bt_rp = c.Bt.rowptr.p; A.B_rp = c.B.rowptr.p; A.Mp_rp = c.Mp.rowptr.p;
   A.F_val = c.F.val.p; A.Bt_val = c.Bt.val.p; A.B_val = c.B.val.p; A.Mp_val = c.Mp.val.p;
   A.cell_vertices = c.cell_vertices.p; A.cell_dofs = c.cell_dofs.p; A.cell_pat = c.cell_pat.p; A.pat_off = c.pat_off.p;
-  A.n_u = c.n_u; A.fe = c.d_fe.p;
+  A.n_u_loc = c.n_u + c.n_ug; A.n_u_own = c.n_u; A.n_p_own = c.n_p; A.vmap = c.vmap.p; A.fe = c.d_fe.p;
+  A.F_sink = c.F.nnz + 12; A.Bt_sink = c.Bt.nnz + 12; A.B_sink = c.B.nnz + 12; A.Mp_sink = c.Mp.nnz + 12;
+  // ghost import of the state the cells read (`solution = solution_owned`, NSSolverStationary.cpp:722)
+  halo_exchange(c, 0, A.sol); halo_exchange(c, 1, A.sol + c.n_u);
+  if (mode >= NSX_MODE_UNSTEADY_FIRST) { halo_exchange(c, 0, A.sol_old); halo_exchange(c, 1, A.sol_old + c.n_u); }
   for (int col = 0; col < c.ncolors; ++col) {
     const int64_t lo = c.color_ptr[col], hi = c.color_ptr[col + 1];
     if (hi == lo) continue;
@@ -552,14 +571,27 @@ void assemble(Ctx &c, int mode, bool apply_inlet, double nu, double dt, double p
 void lift_drag(Ctx &c, double nu, double *drag, double *lift) {
   const int64_t nf = (int64_t)c.h_cyl_cell.size();
   *drag = 0; *lift = 0;
-  if (!nf) return;
-  k_lift_drag<<<(int)((nf + 63) / 64), 64, 0, c.stream>>>(nf, c.cyl_cell.p, c.cyl_face.p, c.d_fe.p, c.cell_vertices.p, c.cell_dofs.p,
-                                                         c.vec[NSX_VEC_SOLUTION].p, nu, c.face_force.p);
-  c.stat_launches++;
-  std::vector<double> h(2 * nf);
-  NSX_CUDA(cudaMemcpyAsync(h.data(), c.face_force.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-  NSX_CUDA(cudaStreamSynchronize(c.stream));
-  for (int64_t k = 0; k < nf; ++k) { *drag += h[2 * k]; *lift += h[2 * k + 1]; }  // face order, as the reference's loop
+  double *sol = c.vec[NSX_VEC_SOLUTION].p;
+  halo_exchange(c, 0, sol); halo_exchange(c, 1, sol + c.n_u);
+  if (nf) {
+    k_lift_drag<<<(int)((nf + 63) / 64), 64, 0, c.stream>>>(nf, c.cyl_cell.p, c.cyl_face.p, c.d_fe.p, c.cell_vertices.p, c.cell_dofs.p, c.vmap.p,
+                                                           sol, nu, c.face_force.p);
+    c.stat_launches++;
+    std::vector<double> h(2 * nf);
+    NSX_CUDA(cudaMemcpyAsync(h.data(), c.face_force.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    NSX_CUDA(cudaStreamSynchronize(c.stream));
+    for (int64_t k = 0; k < nf; ++k) { *drag += h[2 * k]; *lift += h[2 * k + 1]; }  // face order, as the reference's loop
+  }
+  if (c.comm) {  // Utilities::MPI::sum of the two forces (NSSolverStationary.cpp:894-895)
+    const double loc[2] = {*drag, *lift};
+    vec_dot_dev(c, RED_SLOTS - 1, sol, sol, 0);  // makes sure the slot buffer exists (no launch for n = 0)
+    double *slots = slot_ptr(c, RED_SLOTS - 4);
+    NSX_CUDA(cudaMemcpyAsync(slots, loc, sizeof(loc), cudaMemcpyHostToDevice, c.stream));
+    allreduce_slots(c, RED_SLOTS - 4, 2);
+    double out[2];
+    read_slots(c, RED_SLOTS - 4, 2, out);
+    *drag = out[0]; *lift = out[1];
+  }
 }
 
 }  // namespace nsx

@@ -25,16 +25,29 @@ int guarded(nsx_ctx *ctx, Fn &&fn) {
   catch (const std::exception &e) { ctx->err = e.what(); return NSX_E_CUDA; }
 }
 
-void set_block(Ctx &c, DevCSR &A, int64_t nrows, int64_t ncols, const int64_t *rowptr, const int32_t *col) {
+// `cols_are_p`: the block's columns index pressure dofs.  Host copies keep the local column ids; the device
+// copy is baked to the vector layout [u owned | p owned | u ghosts | p ghosts] (relative to the start of the
+// velocity or of the pressure part), so that SpMV kernels index x directly.
+void set_block(Ctx &c, DevCSR &A, int64_t nrows, int64_t ncols, const int64_t *rowptr, const int32_t *col, bool cols_are_p) {
   A.nrows = nrows; A.ncols = ncols;
   A.h_rowptr.assign(rowptr, rowptr + nrows + 1);
   A.nnz = rowptr[nrows];
   A.h_col.assign(col, col + A.nnz);
-  A.rowptr.alloc_padded(A.h_rowptr.size(), 4);
+  for (int64_t k = 0; k < A.nnz; ++k)
+    if (col[k] < 0 || col[k] >= ncols) throw std::invalid_argument("pattern column out of range");
+  A.rowptr.alloc_padded(A.h_rowptr.size(), 4, c.stream);
   NSX_CUDA(cudaMemcpyAsync(A.rowptr.p, A.h_rowptr.data(), A.h_rowptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
-  A.col.alloc_padded(A.nnz, 8);
-  NSX_CUDA(cudaMemcpyAsync(A.col.p, A.h_col.data(), A.nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
-  A.val.alloc_padded(A.nnz, 8);
+  A.col.alloc_padded(A.nnz, 16, c.stream);
+  std::vector<int32_t> baked;
+  const int32_t *dev_col = A.h_col.data();
+  const int64_t own = cols_are_p ? c.n_p : c.n_u, shift = cols_are_p ? c.n_ug : c.n_p;
+  if (c.n_ug + c.n_pg > 0) {
+    baked.resize(A.nnz);
+    for (int64_t k = 0; k < A.nnz; ++k) baked[k] = (int32_t)(col[k] < own ? col[k] : col[k] + shift);
+    dev_col = baked.data();
+  }
+  NSX_CUDA(cudaMemcpyAsync(A.col.p, dev_col, A.nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
+  A.val.alloc_padded(A.nnz, 16, c.stream);  // val[nnz + 12] is the sink of the ghost rows' contributions (assemble.cu)
   A.nrb = A.ndesc = 0;
   c.nrb_u = c.nrb_p = c.ndesc_u = c.ndesc_p = 0;
   A.max_row = 0;
@@ -42,7 +55,7 @@ void set_block(Ctx &c, DevCSR &A, int64_t nrows, int64_t ncols, const int64_t *r
     A.max_row = std::max<int>(A.max_row, (int)(rowptr[i + 1] - rowptr[i]));
     if (!std::is_sorted(col + rowptr[i], col + rowptr[i + 1])) throw std::invalid_argument("pattern rows must have ascending columns");
   }
-  if (nrows == ncols) {
+  if (&A == &c.F || &A == &c.Mp) {  // square blocks: owned rows x (owned + ghost) columns, diagonal among the owned
     std::vector<int32_t> diag(nrows, -1);
     for (int64_t i = 0; i < nrows; ++i) {
       const int32_t *b = col + rowptr[i], *e = col + rowptr[i + 1];
@@ -91,6 +104,7 @@ int nsx_destroy(nsx_ctx *ctx) {
   if (!ctx) return NSX_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  comm_destroy(*ctx);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
   cudaStream_t s = ctx->own_stream ? ctx->stream : nullptr;
   delete ctx;
@@ -110,7 +124,7 @@ int nsx_set_option(nsx_ctx *ctx, int option, int64_t value) {
       case NSX_OPT_ORTHO: ctx->ortho = value ? 1 : 0; break;
       case NSX_OPT_COOP_SWEEP: ctx->coop_sweep = value ? 1 : 0; break;
       case NSX_OPT_STREAM_SPMV:
-        if (value < 0 || value > 2) throw std::invalid_argument("SpMV kernel must be 0, 1 or 2");
+        if (value < 0 || value > 3) throw std::invalid_argument("SpMV kernel must be 0, 1, 2 or 3");
         ctx->stream_spmv = (int)value; break;
       default: throw std::invalid_argument("unknown option");
     }
@@ -135,6 +149,8 @@ int64_t nsx_get_stat(const nsx_ctx *ctx, int stat) {
     case NSX_STAT_ASSEMBLY_COLOURS: return ctx->ncolors;
     case NSX_STAT_ASSEMBLY_TABLES: return ctx->npat;
     case NSX_STAT_LAST_STEP: return ctx->last_step;
+    case NSX_STAT_HALO_EXCHANGES: return ctx->stat_halo;
+    case NSX_STAT_ALLREDUCES: return ctx->stat_allreduce;
   }
   return -1;
 }
@@ -147,13 +163,16 @@ int nsx_set_discretisation(nsx_ctx *ctx, int elem, int64_t n_cells, const double
     Ctx &c = *ctx;
     build_fe_tables(elem, c.fe);
     c.ncells = n_cells; c.n_u = n_u; c.n_p = n_p; c.n = n_u + n_p;
+    c.n_ug = c.n_pg = 0; c.nvec = c.n;
+    c.halo_u = HaloPlan(); c.halo_p = HaloPlan();
+    c.h_cell_owned.clear();
     c.h_cell_vertices.assign(cell_vertices, cell_vertices + (size_t)n_cells * c.fe.nvpc * 2);
     c.h_cell_dofs.assign(cell_dofs, cell_dofs + (size_t)n_cells * c.fe.ndofs);
     for (uint32_t d : c.h_cell_dofs)
-      if ((int64_t)d >= c.n) throw std::invalid_argument("cell dof index out of range");
+      if ((int64_t)d >= n_u + n_p) throw std::invalid_argument("cell dof index out of range");
     c.cell_vertices.upload(c.h_cell_vertices, c.stream);
     c.cell_dofs.upload(c.h_cell_dofs, c.stream);
-    for (auto &v : c.vec) { v.alloc(c.n); v.zero(c.stream); }
+    for (auto &v : c.vec) { v.alloc(c.nvec); v.zero(c.stream); }
     c.owned_u = {0, n_u}; c.owned_p = {0, n_p};
     c.have_disc = true; c.finalized = false; c.S_symbolic = false;
     c.tri.clear();
@@ -166,10 +185,11 @@ int nsx_set_pattern(nsx_ctx *ctx, int block, int64_t nrows, int64_t ncols, const
     Ctx &c = *ctx;
     if (!c.have_disc) throw std::logic_error("nsx_set_discretisation must come first");
     if (!rowptr || !col || block < NSX_BLOCK_F || block > NSX_BLOCK_MP) throw std::invalid_argument("bad pattern block");
+    const bool cols_p = !(block == NSX_BLOCK_F || block == NSX_BLOCK_B);
     const int64_t er = (block == NSX_BLOCK_F || block == NSX_BLOCK_BT) ? c.n_u : c.n_p;
-    const int64_t ec = (block == NSX_BLOCK_F || block == NSX_BLOCK_B) ? c.n_u : c.n_p;
-    if (nrows != er || ncols != ec) throw std::invalid_argument("pattern shape does not match the block");
-    set_block(c, block_ref(c, block), nrows, ncols, rowptr, col);
+    const int64_t ec = cols_p ? c.n_p + c.n_pg : c.n_u + c.n_ug;
+    if (nrows != er || ncols != ec) throw std::invalid_argument("pattern shape does not match the block (owned rows x owned + ghost columns)");
+    set_block(c, block_ref(c, block), nrows, ncols, rowptr, col, cols_p);
     c.finalized = false;
     c.tri.erase(block);
     if (block == NSX_BLOCK_B || block == NSX_BLOCK_BT) { c.S_symbolic = false; c.tri.erase(NSX_BLOCK_S); }
@@ -219,12 +239,68 @@ int nsx_set_ranks(nsx_ctx *ctx, int nranks, const int64_t *owned_u, const int64_
   });
 }
 
+int nsx_set_partition(nsx_ctx *ctx, int64_t n_u_owned, int64_t n_p_owned) {
+  return guarded(ctx, [&] {
+    Ctx &c = *ctx;
+    if (!c.have_disc) throw std::logic_error("nsx_set_discretisation must come first");
+    const int64_t lu = c.n_u + c.n_ug, lp = c.n_p + c.n_pg;  // local (owned + ghost) counts given to nsx_set_discretisation
+    if (n_u_owned <= 0 || n_u_owned > lu || n_p_owned <= 0 || n_p_owned > lp) throw std::invalid_argument("owned counts must lie in (0, local count]");
+    for (int b = NSX_BLOCK_F; b <= NSX_BLOCK_MP; ++b)
+      if (!block_ref(c, b).h_rowptr.empty()) throw std::logic_error("nsx_set_partition must precede nsx_set_pattern");
+    c.n_u = n_u_owned; c.n_p = n_p_owned; c.n = c.n_u + c.n_p;
+    c.n_ug = lu - n_u_owned; c.n_pg = lp - n_p_owned;
+    c.nvec = lu + lp;
+    c.owned_u = {0, c.n_u}; c.owned_p = {0, c.n_p};
+    c.tri.clear();
+    c.finalized = false;
+  });
+}
+
+int nsx_set_halo(nsx_ctx *ctx, int block, int n_neighbours, const int32_t *neighbour, const int64_t *send_ptr, const int32_t *send_idx,
+                 const int64_t *recv_ptr) {
+  return guarded(ctx, [&] {
+    Ctx &c = *ctx;
+    if (!c.have_disc) throw std::logic_error("nsx_set_discretisation must come first");
+    if ((block != 0 && block != 1) || n_neighbours < 0 || (n_neighbours && (!neighbour || !send_ptr || !recv_ptr))) throw std::invalid_argument("bad halo plan");
+    HaloPlan &H = block ? c.halo_p : c.halo_u;
+    H = HaloPlan();
+    const int64_t own = block ? c.n_p : c.n_u, ghosts = block ? c.n_pg : c.n_ug;
+    if (n_neighbours == 0) { if (ghosts) throw std::invalid_argument("ghost dofs without a neighbour to fill them"); return; }
+    if (send_ptr[0] != 0 || recv_ptr[0] != 0 || recv_ptr[n_neighbours] != ghosts) throw std::invalid_argument("halo plan does not cover the ghost dofs");
+    for (int i = 0; i < n_neighbours; ++i) {
+      if (neighbour[i] < 0 || neighbour[i] >= c.nranks || neighbour[i] == c.rank) throw std::invalid_argument("bad neighbour rank");
+      if (send_ptr[i + 1] < send_ptr[i] || recv_ptr[i + 1] < recv_ptr[i]) throw std::invalid_argument("halo ranges must be ascending");
+    }
+    H.nsend = send_ptr[n_neighbours];
+    if (H.nsend && !send_idx) throw std::invalid_argument("bad halo plan");
+    for (int64_t k = 0; k < H.nsend; ++k)
+      if (send_idx[k] < 0 || send_idx[k] >= own) throw std::invalid_argument("only owned dofs can be sent");
+    H.nbr.assign(neighbour, neighbour + n_neighbours);
+    H.send_ptr.assign(send_ptr, send_ptr + n_neighbours + 1);
+    H.recv_ptr.assign(recv_ptr, recv_ptr + n_neighbours + 1);
+    H.send_idx.upload(send_idx, (size_t)H.nsend, c.stream);
+    H.send_buf.alloc((size_t)std::max<int64_t>(1, H.nsend));
+    NSX_CUDA(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int nsx_halo_exchange(nsx_ctx *ctx, int which) {
+  return guarded(ctx, [&] {
+    Ctx &c = *ctx;
+    double *v = vec_of(c, which);
+    halo_exchange(c, 0, v);
+    halo_exchange(c, 1, v + c.n_u);
+    NSX_CUDA(cudaStreamSynchronize(c.stream));
+  });
+}
+
 int nsx_finalize_setup(nsx_ctx *ctx) {
   return guarded(ctx, [&] {
     Ctx &c = *ctx;
     if (!c.have_disc) throw std::logic_error("nsx_set_discretisation must come first");
     for (int b = NSX_BLOCK_F; b <= NSX_BLOCK_MP; ++b)
       if (block_ref(c, b).h_rowptr.empty()) throw std::logic_error("all four block patterns must be set before nsx_finalize_setup");
+    if ((c.n_ug && c.halo_u.nbr.empty()) || (c.n_pg && c.halo_p.nbr.empty())) throw std::logic_error("ghost dofs need nsx_set_halo");
     build_assembly_maps(c);
     c.finalized = true;
   });
@@ -243,6 +319,16 @@ int nsx_vec_download(nsx_ctx *ctx, int which, double *host) {
     if (!host) throw std::invalid_argument("null host pointer");
     NSX_CUDA(cudaMemcpyAsync(host, vec_of(*ctx, which), ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     NSX_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int nsx_vec_download_ghosts(nsx_ctx *ctx, int which, double *host_u_ghosts, double *host_p_ghosts) {
+  return guarded(ctx, [&] {
+    Ctx &c = *ctx;
+    const double *v = vec_of(c, which);
+    if (c.n_ug && host_u_ghosts) NSX_CUDA(cudaMemcpyAsync(host_u_ghosts, v + c.n, c.n_ug * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (c.n_pg && host_p_ghosts) NSX_CUDA(cudaMemcpyAsync(host_p_ghosts, v + c.n + c.n_ug, c.n_pg * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    NSX_CUDA(cudaStreamSynchronize(c.stream));
   });
 }
 

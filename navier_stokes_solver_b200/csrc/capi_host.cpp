@@ -1,6 +1,7 @@
 // C ABI over hostsetup.cpp (see include/nsx_host.h).
 #include <cstring>
 #include <exception>
+#include <stdexcept>
 #include <string>
 
 #include "../../include/nsx_host.h"
@@ -54,6 +55,25 @@ nsx_disc *nsx_disc_from_gmsh(const char *path, int nranks) {
   }
 }
 
+nsx_disc *nsx_disc_local(const nsx_disc *global, int rank) {
+  nsx_disc *h = nullptr;
+  try {
+    if (!global) throw std::invalid_argument("null discretisation");
+    h = new nsx_disc;
+    nsx::build_local_view(global->d, rank, h->d);
+    for (auto &bf : h->d.mesh.bfaces) {
+      h->bfaces_flat.push_back(bf.cell);
+      h->bfaces_flat.push_back(bf.face);
+      h->bfaces_flat.push_back(bf.bid);
+    }
+    return h;
+  } catch (const std::exception &e) {
+    g_host_err = e.what();
+    delete h;
+    return nullptr;
+  }
+}
+
 void nsx_disc_free(nsx_disc *d) { delete d; }
 
 int64_t nsx_disc_info(const nsx_disc *h, int what) {
@@ -70,6 +90,11 @@ int64_t nsx_disc_info(const nsx_disc *h, int what) {
     case NSX_DI_NRANKS: return d.nranks;
     case NSX_DI_NBC: return (int64_t)d.bc_dof.size();
     case NSX_DI_NVPC: return d.mesh.nvpc;
+    case NSX_DI_IS_LOCAL: return d.is_local ? 1 : 0;
+    case NSX_DI_RANK: return d.rank;
+    case NSX_DI_JOB_RANKS: return d.is_local ? d.job_ranks : d.nranks;
+    case NSX_DI_N_U_OWNED: return d.is_local ? d.n_u_owned : d.n_u;
+    case NSX_DI_N_P_OWNED: return d.is_local ? d.n_p_owned : d.n_p;
   }
   return -1;
 }
@@ -104,6 +129,18 @@ const void *nsx_disc_array(const nsx_disc *h, int what, int64_t *count) {
     case NSX_DA_CYL_FACE: RET(d.cylinder_face);
     case NSX_DA_BFACES: RET(h->bfaces_flat);
     case NSX_DA_MATERIAL: RET(d.mesh.material);
+    case NSX_DA_L2G_U: RET(d.l2g_u);
+    case NSX_DA_L2G_P: RET(d.l2g_p);
+    case NSX_DA_CELL_GLOBAL: RET(d.cell_global);
+    case NSX_DA_CELL_OWNED: RET(d.cell_owned);
+    case NSX_DA_HALO_U_NBR: RET(d.halo_u.nbr);
+    case NSX_DA_HALO_U_SEND_PTR: RET(d.halo_u.send_ptr);
+    case NSX_DA_HALO_U_SEND_IDX: RET(d.halo_u.send_idx);
+    case NSX_DA_HALO_U_RECV_PTR: RET(d.halo_u.recv_ptr);
+    case NSX_DA_HALO_P_NBR: RET(d.halo_p.nbr);
+    case NSX_DA_HALO_P_SEND_PTR: RET(d.halo_p.send_ptr);
+    case NSX_DA_HALO_P_SEND_IDX: RET(d.halo_p.send_idx);
+    case NSX_DA_HALO_P_RECV_PTR: RET(d.halo_p.recv_ptr);
     case NSX_DA_FE_TABLES: *count = (int64_t)sizeof(nsx::FETables); return &d.fe;
   }
   *count = 0;

@@ -20,7 +20,10 @@ struct CudaError : std::runtime_error {
 };
 struct NoConvergence : std::runtime_error {
   int last_step; double last_residual;
-  NoConvergence(int s, double r) : std::runtime_error("SolverControl::NoConvergence"), last_step(s), last_residual(r) {}
+  NoConvergence(int s, double r, const char *who = "")
+      : std::runtime_error(std::string("SolverControl::NoConvergence") + (who[0] ? std::string(" in ") + who : std::string()) + " at step " + std::to_string(s) +
+                           ", residual " + std::to_string(r)),
+        last_step(s), last_residual(r) {}
 };
 
 #define NSX_CUDA(call)                                                                          \
@@ -48,10 +51,11 @@ struct DevBuf {
     n = count;
   }
   // `pad` extra elements behind the `count` the buffer reports (bulk copies round their ranges up to 16 bytes)
-  void alloc_padded(size_t count, size_t pad) {
+  // (zeroed on the caller's stream: a legacy-stream memset would race with later copies on a non-blocking stream)
+  void alloc_padded(size_t count, size_t pad, cudaStream_t s) {
     release();
     NSX_CUDA(cudaMalloc(&p, (count + pad) * sizeof(T)));
-    NSX_CUDA(cudaMemset(p, 0, (count + pad) * sizeof(T)));
+    NSX_CUDA(cudaMemsetAsync(p, 0, (count + pad) * sizeof(T), s));
     n = count;
   }
   void upload(const T *h, size_t count, cudaStream_t s) {
@@ -109,6 +113,15 @@ struct TriPlan {
 
 struct AmgHierarchy;  // amg.cu
 
+// Ghost import plan of one block on this rank (the role of Epetra_Import in the reference's ghosted vectors)
+struct HaloPlan {
+  std::vector<int> nbr;                 // neighbour ranks
+  std::vector<int64_t> send_ptr, recv_ptr;
+  DevBuf<int32_t> send_idx;             // owned local ids to pack, grouped by neighbour
+  DevBuf<double> send_buf;
+  int64_t nsend = 0;
+};
+
 struct Ctx {
   int rank = 0, nranks = 1, device = 0;
   cudaStream_t stream = nullptr;
@@ -128,7 +141,15 @@ struct Ctx {
   // discretisation
   FETables fe;
   bool have_disc = false, finalized = false;
-  int64_t ncells = 0, n_u = 0, n_p = 0, n = 0;
+  // n_u / n_p / n count the OWNED dofs of this rank (everything, on one GPU); n_ug / n_pg its ghosts.  Every
+  // vector is allocated with nvec = n + n_ug + n_pg entries, laid out [u owned | p owned | u ghosts | p ghosts]:
+  // BLAS-1 kernels run over the first n entries, SpMV column indices are baked to that layout at set-up.
+  int64_t ncells = 0, n_u = 0, n_p = 0, n = 0, n_ug = 0, n_pg = 0, nvec = 0;
+  HaloPlan halo_u, halo_p;
+  void *comm = nullptr;           // ncclComm_t (comm.cu); null on one GPU
+  int64_t stat_halo = 0, stat_allreduce = 0;
+  DevBuf<int32_t> vmap;           // local block dof id (cell table) -> index in a vector
+  std::vector<uint8_t> h_cell_owned;
   std::vector<double> h_cell_vertices;
   std::vector<uint32_t> h_cell_dofs;
   DevBuf<double> cell_vertices;
@@ -240,6 +261,13 @@ void schur_complement(Ctx &c);  // S = B diag(F)^-1 Bt, fills Dvec / Dinv
 // ---- amg.cu ---------------------------------------------------------------------------------
 void amg_setup(Ctx &c, const DevCSR &A);
 void amg_apply(Ctx &c, double *y, const double *x);
+
+// ---- comm.cu --------------------------------------------------------------------------------
+// blk 0: velocity ghosts of the vector starting at `base` (block or velocity-only vector);
+// blk 1: pressure ghosts of the pressure part starting at `base`.  No-ops on one GPU.
+void halo_exchange(Ctx &c, int blk, const double *base);
+void allreduce_slots(Ctx &c, int slot, int count);   // in-place sum over ranks of device scalar slots
+void comm_destroy(Ctx &c);
 
 // ---- krylov.cu ------------------------------------------------------------------------------
 int solve_system(Ctx &c, int flavour, int solver, int prec, double tol, int max_it, double alpha, double *final_res);

@@ -208,29 +208,37 @@ void partition_strips(Mesh &m, int nranks) {
 
 namespace {
 
-void build_block_pattern(const Discretisation &d, bool row_is_p, bool col_is_p, CSRPattern &P) {
-  const FETables &T = d.fe;
-  const int nc = d.mesh.ncells(), nd = T.ndofs;
-  const int64_t nrows = row_is_p ? d.n_p : d.n_u, ncols = col_is_p ? d.n_p : d.n_u;
-  const uint32_t roff = row_is_p ? (uint32_t)d.n_u : 0u, coff = col_is_p ? (uint32_t)d.n_u : 0u;
+// Sparsity of one block from a cell -> dof table (ids of the pressure block offset by `p_off`); rows at and
+// beyond `nrows` (ghost rows of a local view) are left out.
+void build_block_pattern(const FETables &T, const uint32_t *cell_dofs, int64_t nc, int64_t p_off, bool row_is_p, bool col_is_p,
+                         int64_t nrows, int64_t ncols, CSRPattern &P) {
+  const int nd = T.ndofs;
+  const uint32_t roff = row_is_p ? (uint32_t)p_off : 0u, coff = col_is_p ? (uint32_t)p_off : 0u;
   P.nrows = nrows; P.ncols = ncols;
   // row -> cells adjacency (CSR)
   std::vector<int64_t> rc_ptr(nrows + 1, 0);
-  for (int c = 0; c < nc; ++c)
+  for (int64_t c = 0; c < nc; ++c)
     for (int i = 0; i < nd; ++i)
-      if ((T.dof_comp[i] == 2) == row_is_p) rc_ptr[d.cell_dofs[(size_t)c * nd + i] - roff + 1]++;
+      if ((T.dof_comp[i] == 2) == row_is_p) {
+        const int64_t r = (int64_t)cell_dofs[(size_t)c * nd + i] - roff;
+        if (r < nrows) rc_ptr[r + 1]++;
+      }
   for (int64_t r = 0; r < nrows; ++r) rc_ptr[r + 1] += rc_ptr[r];
-  std::vector<int> rc(rc_ptr[nrows]);
+  std::vector<int32_t> rc(rc_ptr[nrows]);
   {
     std::vector<int64_t> fill(rc_ptr.begin(), rc_ptr.end() - 1);
-    for (int c = 0; c < nc; ++c)
+    for (int64_t c = 0; c < nc; ++c)
       for (int i = 0; i < nd; ++i)
-        if ((T.dof_comp[i] == 2) == row_is_p) rc[fill[d.cell_dofs[(size_t)c * nd + i] - roff]++] = c;
+        if ((T.dof_comp[i] == 2) == row_is_p) {
+          const int64_t r = (int64_t)cell_dofs[(size_t)c * nd + i] - roff;
+          if (r < nrows) rc[fill[r]++] = (int32_t)c;
+        }
   }
   std::vector<int> lcols;
   for (int j = 0; j < nd; ++j)
     if ((T.dof_comp[j] == 2) == col_is_p) lcols.push_back(j);
   P.rowptr.assign(nrows + 1, 0);
+  P.col.clear();
   // pass 1: counts, pass 2: fill
   for (int pass = 0; pass < 2; ++pass) {
 #pragma omp parallel
@@ -240,7 +248,7 @@ void build_block_pattern(const Discretisation &d, bool row_is_p, bool col_is_p, 
       for (int64_t r = 0; r < nrows; ++r) {
         tmp.clear();
         for (int64_t k = rc_ptr[r]; k < rc_ptr[r + 1]; ++k) {
-          const uint32_t *cd = &d.cell_dofs[(size_t)rc[k] * nd];
+          const uint32_t *cd = &cell_dofs[(size_t)rc[k] * nd];
           for (int j : lcols) tmp.push_back((int32_t)(cd[j] - coff));
         }
         std::sort(tmp.begin(), tmp.end());
@@ -348,10 +356,10 @@ void build_discretisation(Discretisation &d) {
     }
   }
   // block sparsity from the coupling table (everything but p-p; p-p only for Mp)
-  build_block_pattern(d, false, false, d.F);
-  build_block_pattern(d, false, true, d.Bt);
-  build_block_pattern(d, true, false, d.B);
-  build_block_pattern(d, true, true, d.Mp);
+  build_block_pattern(T, d.cell_dofs.data(), nc, d.n_u, false, false, d.n_u, d.n_u, d.F);
+  build_block_pattern(T, d.cell_dofs.data(), nc, d.n_u, false, true, d.n_u, d.n_p, d.Bt);
+  build_block_pattern(T, d.cell_dofs.data(), nc, d.n_u, true, false, d.n_p, d.n_u, d.B);
+  build_block_pattern(T, d.cell_dofs.data(), nc, d.n_u, true, true, d.n_p, d.n_p, d.Mp);
 
   // Dirichlet lists: boundary 7 first, then {7, 6, 10}; last writer wins (std::map assignment
   // semantics of interpolate_boundary_values, NSSolverStationary.cpp:560-572).
@@ -397,6 +405,143 @@ void build_discretisation(Discretisation &d) {
     if (bf.bid == 8) { d.outlet_cell.push_back(bf.cell); d.outlet_face.push_back(bf.face); }
     if (bf.bid == 10) { d.cylinder_cell.push_back(bf.cell); d.cylinder_face.push_back(bf.face); }
   }
+}
+
+void build_local_view(const Discretisation &g, int rank, Discretisation &l) {
+  if (g.is_local) throw std::invalid_argument("build_local_view needs the global discretisation");
+  if (rank < 0 || rank >= g.nranks) throw std::invalid_argument("rank outside the partition");
+  const FETables &T = g.fe;
+  const int nd = T.ndofs, nv = g.mesh.nvpc;
+  const int64_t nc = g.mesh.ncells();
+  const int64_t u0 = g.owned_u[rank], u1 = g.owned_u[rank + 1], p0 = g.owned_p[rank], p1 = g.owned_p[rank + 1];
+  auto owner_of = [&](uint32_t d) -> int {  // block-global dof id -> owning rank
+    const bool isp = (int64_t)d >= g.n_u;
+    const std::vector<int64_t> &ow = isp ? g.owned_p : g.owned_u;
+    const int64_t v = isp ? (int64_t)d - g.n_u : (int64_t)d;
+    return (int)(std::upper_bound(ow.begin(), ow.end(), v) - ow.begin()) - 1;
+  };
+  l = Discretisation();
+  l.is_local = true; l.rank = rank; l.job_ranks = g.nranks; l.nranks = 1;
+  l.fe = g.fe;
+  l.mesh.elem = g.mesh.elem; l.mesh.nvpc = nv;
+  l.n_u_owned = u1 - u0; l.n_p_owned = p1 - p0;
+
+  // local cells (global order) and, per neighbour, the owned dofs it needs
+  std::vector<int64_t> ghost_u, ghost_p;
+  std::vector<std::vector<int32_t>> send_u(g.nranks), send_p(g.nranks);
+  std::vector<int> owners(nd);
+  for (int64_t c = 0; c < nc; ++c) {
+    const uint32_t *cd = &g.cell_dofs[(size_t)c * nd];
+    bool mine = false;
+    unsigned long long others = 0;  // bit set of other owner ranks (<= 64 ranks)
+    for (int i = 0; i < nd; ++i) {
+      owners[i] = owner_of(cd[i]);
+      if (owners[i] == rank) mine = true;
+      else others |= 1ull << (owners[i] & 63);
+    }
+    if (!mine) continue;
+    l.cell_global.push_back((int32_t)c);
+    l.cell_owned.push_back(g.mesh.cell_rank[c] == rank);
+    if (!others) continue;
+    for (int i = 0; i < nd; ++i) {
+      const bool isp = T.dof_comp[i] == 2;
+      if (owners[i] == rank) {
+        const int32_t lid = (int32_t)(isp ? (int64_t)cd[i] - g.n_u - p0 : (int64_t)cd[i] - u0);
+        for (int r = 0; r < g.nranks; ++r)
+          if (r != rank && (others >> (r & 63) & 1)) (isp ? send_p : send_u)[r].push_back(lid);
+      } else {
+        (isp ? ghost_p : ghost_u).push_back(isp ? (int64_t)cd[i] - g.n_u : (int64_t)cd[i]);
+      }
+    }
+  }
+  if (g.nranks > 64) throw std::runtime_error("more than 64 ranks are not supported by the host set-up stand-in");
+  auto uniq = [](auto &v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); };
+  uniq(ghost_u); uniq(ghost_p);
+  for (auto &v : send_u) uniq(v);
+  for (auto &v : send_p) uniq(v);
+  l.n_u = l.n_u_owned + (int64_t)ghost_u.size();
+  l.n_p = l.n_p_owned + (int64_t)ghost_p.size();
+  l.l2g_u.resize(l.n_u); l.l2g_p.resize(l.n_p);
+  for (int64_t i = 0; i < l.n_u_owned; ++i) l.l2g_u[i] = u0 + i;
+  for (size_t i = 0; i < ghost_u.size(); ++i) l.l2g_u[l.n_u_owned + i] = ghost_u[i];
+  for (int64_t i = 0; i < l.n_p_owned; ++i) l.l2g_p[i] = p0 + i;
+  for (size_t i = 0; i < ghost_p.size(); ++i) l.l2g_p[l.n_p_owned + i] = ghost_p[i];
+  auto local_u = [&](int64_t gid) -> int64_t {
+    if (gid >= u0 && gid < u1) return gid - u0;
+    return l.n_u_owned + (std::lower_bound(ghost_u.begin(), ghost_u.end(), gid) - ghost_u.begin());
+  };
+  auto local_p = [&](int64_t gid) -> int64_t {
+    if (gid >= p0 && gid < p1) return gid - p0;
+    return l.n_p_owned + (std::lower_bound(ghost_p.begin(), ghost_p.end(), gid) - ghost_p.begin());
+  };
+  // halo plans: ghosts are sorted by global id, i.e. grouped by owner
+  auto plan = [&](Discretisation::Halo &H, const std::vector<int64_t> &ghost, const std::vector<int64_t> &owned,
+                  const std::vector<std::vector<int32_t>> &send) {
+    H.send_ptr.assign(1, 0); H.recv_ptr.assign(1, 0);
+    size_t gpos = 0;
+    for (int r = 0; r < g.nranks; ++r) {
+      size_t gend = gpos;
+      while (gend < ghost.size() && ghost[gend] < owned[r + 1]) ++gend;
+      const bool recv = gend > gpos, snd = !send[r].empty();
+      if (r != rank && (recv || snd)) {
+        H.nbr.push_back(r);
+        H.send_idx.insert(H.send_idx.end(), send[r].begin(), send[r].end());
+        H.send_ptr.push_back((int64_t)H.send_idx.size());
+        H.recv_ptr.push_back((int64_t)gend);
+      } else if (recv) {
+        throw std::runtime_error("ghost dof owned by this rank");
+      }
+      gpos = gend;
+    }
+  };
+  plan(l.halo_u, ghost_u, g.owned_u, send_u);
+  plan(l.halo_p, ghost_p, g.owned_p, send_p);
+
+  // cell tables in local numbering
+  const int64_t lc = (int64_t)l.cell_global.size();
+  l.cell_dofs.resize((size_t)lc * nd);
+  l.cell_vertices.resize((size_t)lc * nv * 2);
+  l.mesh.material.resize(lc);
+  l.mesh.cell_rank.assign(lc, 0);
+  l.mesh.cells.assign((size_t)lc * nv, 0);  // vertex ids are not carried over; ncells() stays valid
+  std::vector<int32_t> g2l_cell(nc, -1);
+  for (int64_t k = 0; k < lc; ++k) {
+    const int64_t c = l.cell_global[k];
+    g2l_cell[c] = (int32_t)k;
+    l.mesh.material[k] = g.mesh.material[c];
+    for (int i = 0; i < nd; ++i) {
+      const uint32_t d = g.cell_dofs[(size_t)c * nd + i];
+      l.cell_dofs[(size_t)k * nd + i] = (T.dof_comp[i] == 2) ? (uint32_t)(l.n_u + local_p((int64_t)d - g.n_u)) : (uint32_t)local_u(d);
+    }
+    std::copy(&g.cell_vertices[(size_t)c * nv * 2], &g.cell_vertices[(size_t)(c + 1) * nv * 2], &l.cell_vertices[(size_t)k * nv * 2]);
+  }
+  l.owned_u = {0, l.n_u_owned};
+  l.owned_p = {0, l.n_p_owned};
+  // owned rows of the four blocks, local columns
+  build_block_pattern(T, l.cell_dofs.data(), lc, l.n_u, false, false, l.n_u_owned, l.n_u, l.F);
+  build_block_pattern(T, l.cell_dofs.data(), lc, l.n_u, false, true, l.n_u_owned, l.n_p, l.Bt);
+  build_block_pattern(T, l.cell_dofs.data(), lc, l.n_u, true, false, l.n_p_owned, l.n_u, l.B);
+  build_block_pattern(T, l.cell_dofs.data(), lc, l.n_u, true, true, l.n_p_owned, l.n_p, l.Mp);
+  // boundary lists: owned constrained dofs; outlet faces of every local cell (their owned rows take the term);
+  // cylinder faces of this rank's own cells (compute_lift_drag loops locally owned cells)
+  for (size_t k = 0; k < g.bc_dof.size(); ++k) {
+    const int64_t d = g.bc_dof[k];
+    if (d < u0 || d >= u1) continue;
+    l.bc_dof.push_back((uint32_t)(d - u0));
+    l.bc_shape.push_back(g.bc_shape[k]);
+    l.bc_on_inlet.push_back(g.bc_on_inlet[k]);
+    l.bc_y.push_back(g.bc_y[k]);
+  }
+  for (size_t k = 0; k < g.outlet_cell.size(); ++k) {
+    const int32_t lcid = g2l_cell[g.outlet_cell[k]];
+    if (lcid >= 0) { l.outlet_cell.push_back(lcid); l.outlet_face.push_back(g.outlet_face[k]); }
+  }
+  for (size_t k = 0; k < g.cylinder_cell.size(); ++k) {
+    const int c = g.cylinder_cell[k];
+    if (g.mesh.cell_rank[c] == rank) { l.cylinder_cell.push_back(g2l_cell[c]); l.cylinder_face.push_back(g.cylinder_face[k]); }
+  }
+  for (const BFace &bf : g.mesh.bfaces)
+    if (g2l_cell[bf.cell] >= 0) l.mesh.bfaces.push_back({g2l_cell[bf.cell], bf.face, bf.bid});
 }
 
 }  // namespace nsx

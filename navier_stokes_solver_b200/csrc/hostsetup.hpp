@@ -53,6 +53,23 @@ struct Discretisation {
   // boundary faces by id
   std::vector<int> outlet_cell, outlet_face;      // boundary id 8
   std::vector<int> cylinder_cell, cylinder_face;  // boundary id 10
+
+  // ---- one rank's share (build_local_view); unused in the global discretisation ----
+  // Local numbering per block: owned dofs first (global order), then ghosts ascending by global id, which
+  // groups them by owner because owned ranges are contiguous.  In a local view n_u / n_p count owned + ghost
+  // dofs, cell_dofs / patterns / boundary lists use local ids, and the patterns hold the owned rows only.
+  bool is_local = false;
+  int rank = 0, job_ranks = 1;
+  int64_t n_u_owned = 0, n_p_owned = 0;
+  std::vector<int64_t> l2g_u, l2g_p;     // local -> global id inside the block
+  std::vector<int32_t> cell_global;      // local cell -> global cell
+  std::vector<uint8_t> cell_owned;       // 1 where the cell's subdomain is this rank
+  struct Halo {                          // ghost import plan of one block (what Epetra_Import holds in the reference)
+    std::vector<int32_t> nbr;            // neighbour ranks, ascending
+    std::vector<int64_t> send_ptr;       // per neighbour: range in send_idx
+    std::vector<int32_t> send_idx;       // owned local ids whose values the neighbour needs, ascending
+    std::vector<int64_t> recv_ptr;       // per neighbour: range of ghost slots (0 = first ghost) it fills
+  } halo_u, halo_p;
 };
 
 // Rectangular channel 2.2 x 0.41 with nx x ny cells, cells whose centre lies inside the circle
@@ -71,5 +88,12 @@ void partition_strips(Mesh &m, int nranks);
 
 // FE + DoF numbering + sparsity + boundary lists (NSSolverStationary.cpp:114-314).
 void build_discretisation(Discretisation &d);
+
+// The share of rank `rank` of a partitioned discretisation: the cells that touch one of its dofs (its own cells
+// plus a one-cell ghost layer, so that every owned matrix row can be assembled without exchanging matrix
+// values), local dof numbering, owned-row sparsity, ghost import plans and the local boundary lists
+// (reference: locally_owned / locally_relevant IndexSets, NSSolverStationary.cpp:226-242, and the
+// mpi_communicator-aware sparsity at :276-305).
+void build_local_view(const Discretisation &g, int rank, Discretisation &l);
 
 }  // namespace nsx

@@ -174,9 +174,24 @@ void build_row_blocks(Ctx &c, const DevCSR &A1, const DevCSR *A2, DevBuf<int32_t
 // dedicated producer warp keeps full.  The HBM stream no longer depends on how long the consumer
 // warps stall on the x gather: up to (TS-1) x 24 KB per CTA are in flight at any time.  One
 // persistent CTA pair per SM walks the row blocks grid-strided.
-constexpr int TS = 3;                 // ring stages
-constexpr int TNNZ = 1024;            // non-zeros per row block
-constexpr int TROWS = 128;            // rows per row block at most
+#ifndef NSX_TS
+#define NSX_TS 3
+#endif
+#ifndef NSX_TNNZ
+#define NSX_TNNZ 1024
+#endif
+#ifndef NSX_DL
+#define NSX_DL 16
+#endif
+#ifndef NSX_TMINB
+#define NSX_TMINB 4
+#endif
+constexpr int TS = NSX_TS;            // ring stages
+constexpr int TNNZ = NSX_TNNZ;        // non-zeros per row block
+#ifndef NSX_TROWS
+#define NSX_TROWS (NSX_TNNZ / 8)
+#endif
+constexpr int TROWS = NSX_TROWS;      // rows per row block at most
 constexpr int TCAP = TNNZ + 16;       // elements per stage (two segments, each padded to a multiple of 4 at both ends)
 constexpr int TRP = TROWS + 4;        // row pointers per matrix per stage (range padded to even ends)
 constexpr int TCONS = 256;            // consumer threads (8 warps) + 1 producer warp
@@ -222,6 +237,7 @@ __device__ __forceinline__ TmaStage stage_of(unsigned char *ring, int st) {
 
 // Row blocks `first, first + stride, ...` of a list whose entries are of kind 0 (matrices M[0] and, if it has
 // non-zeros there, M[1] share the rows; y offset 0) or kind 1 (matrix M[2] alone; y offset yoff1).
+template <bool DIRECT>
 __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, int first, int stride, int nb, const StreamMat *M,
                                          double *__restrict__ y, int64_t yoff1, int add, unsigned char *ring, uint64_t *full, uint64_t *empty,
                                          RowBlockDesc *pdesc) {
@@ -233,28 +249,32 @@ __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, 
       __syncwarp();
       if (it0 + lane < nit) pdesc[lane] = desc[first + (it0 + lane) * stride];
       __syncwarp();
-      if (lane == 0)
-        for (int it = it0; it < min(nit, it0 + 32); ++it) {
-          const int st = it % TS, use = it / TS;
-          if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
-          const RowBlockDesc d = pdesc[it - it0];
-          const StreamMat &A1 = M[d.kind ? 2 : 0], &A2 = M[1];
-          const bool two = d.kind == 0 && d.c2 > 0;
-          const TmaStage S = stage_of(ring, st);
-          const int ra = d.r0 & ~1, rc = ((d.r1 + 2) & ~1) - ra;  // even-aligned range of row pointers covering [r0, r1]
-          mbar_expect_tx(&full[st], (uint32_t)(d.c1 + (two ? d.c2 : 0)) * 12u + (uint32_t)rc * 8u * (two ? 2u : 1u) + (uint32_t)sizeof(RowBlockDesc));
-          bulk_g2s((void *)S.desc, desc + first + it * stride, sizeof(RowBlockDesc), &full[st]);
-          bulk_g2s(S.rp1, A1.rp + ra, rc * 8, &full[st]);
-          if (d.c1) {
-            bulk_g2s(S.val, A1.val + d.a1, d.c1 * 8, &full[st]);
-            bulk_g2s(S.col, A1.col + d.a1, d.c1 * 4, &full[st]);
-          }
-          if (two) {
-            bulk_g2s(S.rp2, A2.rp + ra, rc * 8, &full[st]);
-            bulk_g2s(S.val + d.c1, A2.val + d.a2, d.c2 * 8, &full[st]);
-            bulk_g2s(S.col + d.c1, A2.col + d.a2, d.c2 * 4, &full[st]);
-          }
+      for (int it = it0; it < min(nit, it0 + 32); ++it) {
+        const int st = it % TS, use = it / TS;
+        if (use > 0 && lane == 0) mbar_wait(&empty[st], (use - 1) & 1);
+        __syncwarp();
+        const RowBlockDesc d = pdesc[it - it0];
+        const StreamMat &A1 = M[d.kind ? 2 : 0], &A2 = M[1];
+        const bool two = d.kind == 0 && d.c2 > 0;
+        const TmaStage S = stage_of(ring, st);
+        const int ra = d.r0 & ~1, rc = ((d.r1 + 2) & ~1) - ra;  // even-aligned range of row pointers covering [r0, r1]
+        // the stage's (up to) seven bulk copies are issued by seven lanes in one go
+        void *dst = nullptr; const void *src = nullptr; uint32_t bytes = 0;
+        switch (lane) {
+          case 0: dst = (void *)S.desc; src = desc + first + it * stride; bytes = sizeof(RowBlockDesc); break;
+          case 1: dst = S.rp1; src = A1.rp + ra; bytes = rc * 8; break;
+          case 2: dst = S.val; src = A1.val + d.a1; bytes = d.c1 * 8; break;
+          case 3: dst = S.col; src = A1.col + d.a1; bytes = d.c1 * 4; break;
+          case 4: if (two) { dst = S.rp2; src = A2.rp + ra; bytes = rc * 8; } break;
+          case 5: if (two) { dst = S.val + d.c1; src = A2.val + d.a2; bytes = d.c2 * 8; } break;
+          case 6: if (two) { dst = S.col + d.c1; src = A2.col + d.a2; bytes = d.c2 * 4; } break;
+          default: break;
         }
+        if (lane == 0)
+          mbar_expect_tx(&full[st], (uint32_t)(d.c1 + (two ? d.c2 : 0)) * 12u + (uint32_t)rc * 8u * (two ? 2u : 1u) + (uint32_t)sizeof(RowBlockDesc));
+        __syncwarp();
+        if (bytes) bulk_g2s(dst, src, bytes, &full[st]);
+      }
     }
     return;
   }
@@ -267,6 +287,43 @@ __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, 
     const double *__restrict__ x1 = M[d.kind ? 2 : 0].x, *__restrict__ x2 = M[1].x;
     double *v = S.val;
     const int32_t *cidx = S.col;
+    double *yy = y + (d.kind ? yoff1 : 0);
+    const int64_t s1 = d.a1, s2 = d.a2 - d.c1;  // stage index = global index - s
+    const int nr = d.r1 - d.r0, roff = d.r0 & 1;
+    if (DIRECT) {
+      // a sub-warp of DL lanes walks each row straight out of the stage: value and column come from shared
+      // memory (filled by the TMA engine, never written by the SM), x through the read-only path, the sum
+      // stays in registers.  No product round trip through shared memory, no CTA-wide barrier.
+      constexpr int DL = NSX_DL;
+      const int sl = tid & (DL - 1);
+      const unsigned hmask = DL == 32 ? 0xffffffffu : ((1u << (DL & 31)) - 1u) << (tid & (32 - DL) & 31);  // sub-warps leave the row loop independently
+      for (int i = tid / DL; i < nr; i += TCONS / DL) {
+        const int b1 = (int)(S.rp1[roff + i] - s1), e1 = (int)(S.rp1[roff + i + 1] - s1);
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        // four predicated gathers in flight per lane and trip; the trip count is uniform over the sub-warp
+        for (int k = b1 + sl; k - sl < e1; k += 4 * DL) {
+          const bool p0 = k < e1, p1 = k + DL < e1, p2 = k + 2 * DL < e1, p3 = k + 3 * DL < e1;
+          const int c0 = p0 ? cidx[k] : 0, c1 = p1 ? cidx[k + DL] : 0, c2 = p2 ? cidx[k + 2 * DL] : 0, c3 = p3 ? cidx[k + 3 * DL] : 0;
+          const double x0 = p0 ? __ldg(x1 + c0) : 0.0, x1v = p1 ? __ldg(x1 + c1) : 0.0, x2v = p2 ? __ldg(x1 + c2) : 0.0, x3v = p3 ? __ldg(x1 + c3) : 0.0;
+          const double v0 = p0 ? v[k] : 0.0, v1 = p1 ? v[k + DL] : 0.0, v2 = p2 ? v[k + 2 * DL] : 0.0, v3 = p3 ? v[k + 3 * DL] : 0.0;
+          a0 += v0 * x0; a1 += v1 * x1v; a2 += v2 * x2v; a3 += v3 * x3v;
+        }
+        if (two) {
+          const int b2 = (int)(S.rp2[roff + i] - s2), e2 = (int)(S.rp2[roff + i + 1] - s2);
+          for (int q = b2 + sl; q - sl < e2; q += 2 * DL) {
+            const bool p0 = q < e2, p1 = q + DL < e2;
+            const int c0 = p0 ? cidx[q] : 0, c1 = p1 ? cidx[q + DL] : 0;
+            const double x0 = p0 ? __ldg(x2 + c0) : 0.0, x1v = p1 ? __ldg(x2 + c1) : 0.0;
+            const double v0 = p0 ? v[q] : 0.0, v1 = p1 ? v[q + DL] : 0.0;
+            a2 += v0 * x0; a3 += v1 * x1v;
+          }
+        }
+        double s = (a0 + a1) + (a2 + a3);
+#pragma unroll
+        for (int o = DL >> 1; o > 0; o >>= 1) s += __shfl_down_sync(hmask, s, o, DL);
+        if (sl == 0) yy[d.r0 + i] = add ? yy[d.r0 + i] + s : s;
+      }
+    } else {
     // phase 1: products in place (every consumer thread busy, four independent gathers each)
 #pragma unroll 4
     for (int k = d.o1 + tid; k < d.o1 + d.n1; k += TCONS) v[k] *= __ldg(x1 + cidx[k]);
@@ -278,9 +335,7 @@ __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, 
     // phase 2: a sub-warp of SG lanes reduces each row's segment(s); row pointers come from the stage
     constexpr int L = SG;
     const int sl = tid & (L - 1);
-    const int64_t s1 = d.a1, s2 = d.a2 - d.c1;  // stage index = global index - s
-    const int nr = d.r1 - d.r0, rpp = TCONS / L, passes = (nr + rpp - 1) / rpp, roff = d.r0 & 1;
-    double *yy = y + (d.kind ? yoff1 : 0);
+    const int rpp = TCONS / L, passes = (nr + rpp - 1) / rpp;
     for (int ps = 0; ps < passes; ++ps) {
       const int i = ps * rpp + tid / L;
       double s = 0;
@@ -297,6 +352,7 @@ __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, 
       if (i < nr && sl == 0) yy[d.r0 + i] = add ? yy[d.r0 + i] + s : s;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes (products) before the TMA's next write
+    }
     // release the stage (this warp's reads are done; the mbarrier orders them before the TMA's next write)
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
@@ -305,7 +361,8 @@ __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, 
 
 // y = A x (kind-0 blocks with one matrix), or jacobian_matrix.vmult with M = {F, Bt, B}: the row blocks of the
 // velocity rows (F + Bt, kind 0) come first in the list, then those of the pressure rows (B, kind 1)
-__global__ void __launch_bounds__(TCONS + 32, 4) k_spmv_tma(const RowBlockDesc *__restrict__ desc, int nb, StreamMat M0, StreamMat M1, StreamMat M2,
+template <bool DIRECT>
+__global__ void __launch_bounds__(TCONS + 32, NSX_TMINB) k_spmv_tma(const RowBlockDesc *__restrict__ desc, int nb, StreamMat M0, StreamMat M1, StreamMat M2,
                                                             double *__restrict__ y, int64_t yoff1, int add) {
   extern __shared__ __align__(128) unsigned char tma_smem[];
   __shared__ RowBlockDesc pdesc[32];
@@ -317,7 +374,7 @@ __global__ void __launch_bounds__(TCONS + 32, 4) k_spmv_tma(const RowBlockDesc *
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  tma_rows(desc, blockIdx.x, gridDim.x, nb, M, y, yoff1, add, tma_smem, full, empty, pdesc);
+  tma_rows<DIRECT>(desc, blockIdx.x, gridDim.x, nb, M, y, yoff1, add, tma_smem, full, empty, pdesc);
 }
 
 void append_row_descs(std::vector<RowBlockDesc> &h, const DevCSR &A1, const DevCSR *A2, int kind) {
@@ -353,7 +410,8 @@ void append_row_descs(std::vector<RowBlockDesc> &h, const DevCSR &A1, const DevC
 void tma_attr_once() {
   static bool done = false;
   if (done) return;
-  NSX_CUDA(cudaFuncSetAttribute(k_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+  NSX_CUDA(cudaFuncSetAttribute(k_spmv_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+  NSX_CUDA(cudaFuncSetAttribute(k_spmv_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
   done = true;
 }
 
@@ -369,7 +427,8 @@ inline int pick_group(const DevCSR &A) {
 void spmv(Ctx &c, const DevCSR &A_, const double *x, double *y, bool add) {
   DevCSR &A = const_cast<DevCSR &>(A_);
   if (!A.nrows) return;
-  if (c.stream_spmv == 2 && !A.h_rowptr.empty() && A.nrows < (int64_t)1 << 31) {
+  halo_exchange(c, (&A_ == &c.F || &A_ == &c.B) ? 0 : 1, x);  // ghost import of the input (no-op on one GPU)
+  if (c.stream_spmv >= 2 && !A.h_rowptr.empty() && A.nrows < (int64_t)1 << 31) {
     tma_attr_once();
     if (!A.ndesc) {
       std::vector<RowBlockDesc> h;
@@ -377,9 +436,10 @@ void spmv(Ctx &c, const DevCSR &A_, const double *x, double *y, bool add) {
       A.ndesc = (int)h.size();
       A.desc.upload(h, c.stream);
     }
-    const int grid = std::min(A.ndesc, 4 * c.num_sms);
+    const int grid = std::min(A.ndesc, NSX_TMINB * c.num_sms);
     const StreamMat M{A.rowptr.p, A.col.p, A.val.p, x};
-    k_spmv_tma<<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0);
+    if (c.stream_spmv == 3) k_spmv_tma<true><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0);
+    else k_spmv_tma<false><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0);
     c.stat_launches++; c.stat_spmv++;
     return;
   }
@@ -400,7 +460,9 @@ void spmv(Ctx &c, const DevCSR &A_, const double *x, double *y, bool add) {
 
 void block_spmv(Ctx &c, const double *x, double *y) {
   const int64_t n = c.n_u + c.n_p;
-  if (c.stream_spmv == 2 && n < (int64_t)1 << 31) {
+  halo_exchange(c, 0, x);
+  halo_exchange(c, 1, x + c.n_u);
+  if (c.stream_spmv >= 2 && n < (int64_t)1 << 31) {
     tma_attr_once();
     if (!c.ndesc_u) {
       std::vector<RowBlockDesc> h;
@@ -409,10 +471,10 @@ void block_spmv(Ctx &c, const double *x, double *y) {
       c.ndesc_u = (int)h.size();
       c.desc_u.upload(h, c.stream);
     }
-    const int grid = std::min(c.ndesc_u, 4 * c.num_sms);
-    k_spmv_tma<<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(c.desc_u.p, c.ndesc_u, StreamMat{c.F.rowptr.p, c.F.col.p, c.F.val.p, x},
-                                                         StreamMat{c.Bt.rowptr.p, c.Bt.col.p, c.Bt.val.p, x + c.n_u},
-                                                         StreamMat{c.B.rowptr.p, c.B.col.p, c.B.val.p, x}, y, c.n_u, 0);
+    const int grid = std::min(c.ndesc_u, NSX_TMINB * c.num_sms);
+    const StreamMat MF{c.F.rowptr.p, c.F.col.p, c.F.val.p, x}, MBt{c.Bt.rowptr.p, c.Bt.col.p, c.Bt.val.p, x + c.n_u}, MB{c.B.rowptr.p, c.B.col.p, c.B.val.p, x};
+    if (c.stream_spmv == 3) k_spmv_tma<true><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(c.desc_u.p, c.ndesc_u, MF, MBt, MB, y, c.n_u, 0);
+    else k_spmv_tma<false><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(c.desc_u.p, c.ndesc_u, MF, MBt, MB, y, c.n_u, 0);
     c.stat_launches++; c.stat_spmv++;
     return;
   }

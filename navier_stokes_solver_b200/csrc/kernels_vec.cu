@@ -231,11 +231,13 @@ void vec_multi_dot_dev(Ctx &c, int slot0, const VecList &V, int k, const double 
   if (k < 1 || k > 31) throw std::invalid_argument("multi-dot handles 1..31 vectors");
   k_multi_dot<<<vgrid(c, n), VT, 0, c.stream>>>(V, k, w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot0));
   LAUNCHED(c);
+  allreduce_slots(c, slot0, k);
 }
 void vec_multi_axpy_norm_dev(Ctx &c, int slot_norm, const VecList &V, int k, int slot_coef, double *w, int64_t n) {
   ensure_red(c);
   k_multi_axpy_norm<<<vgrid(c, n), VT, 0, c.stream>>>(V, k, slot_ptr(c, slot_coef), w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot_norm));
   LAUNCHED(c);
+  allreduce_slots(c, slot_norm, 1);
 }
 
 static void ensure_red(Ctx &c) {
@@ -251,15 +253,15 @@ static void ensure_red(Ctx &c) {
 
 void vec_dot_dev(Ctx &c, int slot, const double *a, const double *b, int64_t n) {
   ensure_red(c);
-  if (!n) { NSX_CUDA(cudaMemsetAsync(slot_ptr(c, slot), 0, sizeof(double), c.stream)); return; }
-  k_dot<0><<<vgrid(c, n), VT, 0, c.stream>>>(a, b, nullptr, 0.0, nullptr, nullptr, nullptr, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot));
-  LAUNCHED(c);
+  if (!n) NSX_CUDA(cudaMemsetAsync(slot_ptr(c, slot), 0, sizeof(double), c.stream));
+  else { k_dot<0><<<vgrid(c, n), VT, 0, c.stream>>>(a, b, nullptr, 0.0, nullptr, nullptr, nullptr, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot)); LAUNCHED(c); }
+  allreduce_slots(c, slot, 1);
 }
 void vec_add_and_dot_dev(Ctx &c, int slot, double *w, double sign, const double *dev_coef, const double *x, const double *v, int64_t n) {
   ensure_red(c);
-  if (!n) { NSX_CUDA(cudaMemsetAsync(slot_ptr(c, slot), 0, sizeof(double), c.stream)); return; }
-  k_dot<1><<<vgrid(c, n), VT, 0, c.stream>>>(nullptr, nullptr, w, sign, dev_coef, x, v, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot));
-  LAUNCHED(c);
+  if (!n) NSX_CUDA(cudaMemsetAsync(slot_ptr(c, slot), 0, sizeof(double), c.stream));
+  else { k_dot<1><<<vgrid(c, n), VT, 0, c.stream>>>(nullptr, nullptr, w, sign, dev_coef, x, v, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot)); LAUNCHED(c); }
+  allreduce_slots(c, slot, 1);
 }
 double read_slot(Ctx &c, int slot) {
   ensure_red(c);

@@ -42,7 +42,7 @@ struct Work {
   Work(Ctx &ctx, std::vector<DevBuf<double>> &p, int64_t n_) : c(ctx), pool(p), n(n_) {}
   double *vec(size_t i) {
     if (pool.size() <= i) pool.resize(i + 1);
-    if (pool[i].n != (size_t)n) pool[i].alloc(n);
+    if (pool[i].n != (size_t)c.nvec) pool[i].alloc(c.nvec);  // room for the ghost tail of an SpMV input
     return pool[i].p;
   }
 };
@@ -94,7 +94,7 @@ void solver_cg(Ctx &c, Control &ctl, const DOp &A, double *x, const double *b, c
   else vec_equ(c, g, -1.0, b, n);
   double res = vec_norm(c, g, n);
   State conv = ctl.check(0, res);
-  if (conv != ITERATE) { if (conv != SUCCESS) throw NoConvergence(it, res); return; }
+  if (conv != ITERATE) { if (conv != SUCCESS) throw NoConvergence(it, res, "CG (start)"); return; }
   M(h, g);
   vec_equ(c, d, -1.0, h, n);
   double gh = vec_dot(c, g, h, n);
@@ -113,7 +113,7 @@ void solver_cg(Ctx &c, Control &ctl, const DOp &A, double *x, const double *b, c
     beta = gh / beta;
     vec_sadd(c, d, beta, -1.0, h, n);
   }
-  if (conv != SUCCESS) throw NoConvergence(it, res);
+  if (conv != SUCCESS) throw NoConvergence(it, res, "CG");
 }
 
 // SolverFGMRES::solve (max_basis_size = 30)
@@ -172,7 +172,7 @@ void solver_fgmres(Ctx &c, Control &ctl, const DOp &A, double *x, const double *
     }
     for (size_t j = 0; j < y.size(); ++j) vec_axpy(c, x, y[j], z((int)j), n);
   } while (state == ITERATE);
-  if (state != SUCCESS) throw NoConvergence(accumulated_iterations, res);
+  if (state != SUCCESS) throw NoConvergence(accumulated_iterations, res, slot0 ? "inner FGMRES" : "FGMRES");
 }
 
 // SolverGMRES::solve (max_n_tmp_vectors = 30, left preconditioning, preconditioned residual,
@@ -274,7 +274,7 @@ void solver_gmres(Ctx &c, Control &ctl, const DOp &A, double *x, const double *b
     }
     for (int i = 0; i < dim; ++i) vec_axpy(c, x, yv[i], tmp(i), n);
   } while (state == ITERATE);
-  if (state != SUCCESS) throw NoConvergence(accumulated_iterations, last_res);
+  if (state != SUCCESS) throw NoConvergence(accumulated_iterations, last_res, "GMRES");
 }
 
 // SolverBicgstab::solve (exact_residual = true; breakdown threshold of deal.II >= 9.4)
@@ -331,7 +331,7 @@ void solver_bicgstab(Ctx &c, Control &ctl, const DOp &A, double *x, const double
       state = ctl.check(step, res);
     } while (state == ITERATE);
   } while (breakdown);
-  if (state != SUCCESS) throw NoConvergence(step, res);
+  if (state != SUCCESS) throw NoConvergence(step, res, "BiCGStab");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -366,11 +366,11 @@ struct Preconditioner {
       F = &tri_plan(c, NSX_BLOCK_F); S = &tri_plan(c, NSX_BLOCK_S);
       ilu0_factor(c, *F, c.F);
       ilu0_factor(c, *S, c.S);
-      c.delta_p.alloc(c.n_p);
+      c.delta_p.alloc(c.nvec);
       c.delta_p.zero(c.stream);
     }
-    c.tmp_u.alloc(c.n_u);
-    c.tmp_p.alloc(c.n_p);
+    c.tmp_u.alloc(c.nvec);
+    c.tmp_p.alloc(c.nvec);
   }
 
   void vmult(double *dst, const double *src) {

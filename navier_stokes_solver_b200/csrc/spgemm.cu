@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(256) k_schur(int64_t n_p, const int64_t *__res
 
 void schur_symbolic(Ctx &c) {
   if (c.S_symbolic) return;
+  if (c.n_ug || c.n_pg)
+    throw std::logic_error("aSIMPLE on a partitioned system needs the ghost rows of Bt (B diag(F)^-1 Bt reaches two cells deep); not built in this round");
   const DevCSR &B = c.B, &Bt = c.Bt;
   DevCSR &S = c.S;
   const int64_t n = c.n_p;
@@ -81,12 +83,12 @@ void schur_symbolic(Ctx &c) {
     auto it = std::lower_bound(rows[i].begin(), rows[i].end(), (int32_t)i);
     if (it != rows[i].end() && *it == i) diag[i] = (int32_t)(it - rows[i].begin());
   }
-  S.rowptr.alloc_padded(S.h_rowptr.size(), 4);
+  S.rowptr.alloc_padded(S.h_rowptr.size(), 4, c.stream);
   NSX_CUDA(cudaMemcpyAsync(S.rowptr.p, S.h_rowptr.data(), S.h_rowptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
-  S.col.alloc_padded(S.nnz, 8);
+  S.col.alloc_padded(S.nnz, 16, c.stream);
   NSX_CUDA(cudaMemcpyAsync(S.col.p, S.h_col.data(), S.nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
   S.diag.upload(diag, c.stream);
-  S.val.alloc_padded(S.nnz, 8);
+  S.val.alloc_padded(S.nnz, 16, c.stream);
   c.Dvec.alloc(c.n_u);
   c.Dinv.alloc(c.n_u);
   NSX_CUDA(cudaStreamSynchronize(c.stream));

@@ -282,8 +282,9 @@ TriPlan &tri_plan(Ctx &c, int block) {
   P.ordering = c.ordering;
   const int64_t n = A.nrows;
   P.n = n;
-  // owned range of each row
-  std::vector<int32_t> range(n);
+  // owned range of each row; ghost columns (local ids >= n on a partitioned system) belong to no range, so
+  // the plan keeps exactly the rank-local diagonal block, as Ifpack does with overlap 0
+  std::vector<int32_t> range(std::max<int64_t>(n, A.ncols), -1);
   for (size_t r = 0; r + 1 < owned.size(); ++r)
     for (int64_t i = owned[r]; i < owned[r + 1]; ++i) range[i] = (int32_t)r;
   // elimination order

@@ -113,7 +113,7 @@ def test_spmv_kernel_variants_agree(setup):
     d, orc, dev = setup
     x = np.random.default_rng(8).uniform(-1, 1, d.n)
     ref = orc.spmv(N.BLOCK_J, x)
-    for flag in (0, 1, 2):
+    for flag in (0, 1, 2, 3):
         dev.set_option(N.OPT_STREAM_SPMV, flag)
         assert rel(dev.spmv(N.BLOCK_J, x), ref) < 1e-13
         assert rel(dev.spmv(N.BLOCK_F, x[: d.n_u]), orc.spmv(N.BLOCK_F, x[: d.n_u])) < 1e-13

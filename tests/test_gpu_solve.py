@@ -79,7 +79,7 @@ def test_error_codes():
     rc, _, _ = dev.solve(N.STATIONARY, 1, 7, 1e-10, 100)   # std::invalid_argument in the reference
     assert rc == N.NSX_E_BADARG
     rc, it, res = dev.solve(N.STATIONARY, 1, 2, 1e-30, 3)   # SolverControl::NoConvergence
-    assert rc == N.NSX_E_NOCONV and it == 3 and res > 0
+    assert rc == N.NSX_E_NOCONV and it == 3 and res > 0, dev.last_error()
     # solver outside {0,1,2}: the reference solves nothing and returns last_step() = 0
     rc, it, _ = dev.solve(N.STATIONARY, 5, 2, 1e-10, 100)
     assert rc == N.NSX_OK and it == 0
