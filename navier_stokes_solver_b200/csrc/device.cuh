@@ -235,6 +235,7 @@ double vec_add_and_dot(Ctx &c, double *w, double a, const double *x, const doubl
 
 // ---- kernels_spmv.cu ------------------------------------------------------------------------
 void spmv(Ctx &c, const DevCSR &A, const double *x, double *y, bool add = false);
+void spmv_local(Ctx &c, const DevCSR &A, const double *x, double *y, bool add = false);  // no ghost import (rank-local operators)
 void block_spmv(Ctx &c, const double *x, double *y);  // y_u = F x_u + Bt x_p ; y_p = B x_u
 void extract_diag(Ctx &c, const DevCSR &A, double *d, double *dinv);
 void spmv_probe(Ctx &c, const DevCSR &A, int what, const double *x, double *sink);  // measurement only

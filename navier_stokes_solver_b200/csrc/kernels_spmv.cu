@@ -425,9 +425,14 @@ inline int pick_group(const DevCSR &A) {
 }  // namespace
 
 void spmv(Ctx &c, const DevCSR &A_, const double *x, double *y, bool add) {
+  if (!A_.nrows) return;
+  halo_exchange(c, (&A_ == &c.F || &A_ == &c.B) ? 0 : 1, x);  // ghost import of the input (no-op on one GPU)
+  spmv_local(c, A_, x, y, add);
+}
+
+void spmv_local(Ctx &c, const DevCSR &A_, const double *x, double *y, bool add) {
   DevCSR &A = const_cast<DevCSR &>(A_);
   if (!A.nrows) return;
-  halo_exchange(c, (&A_ == &c.F || &A_ == &c.B) ? 0 : 1, x);  // ghost import of the input (no-op on one GPU)
   if (c.stream_spmv >= 2 && !A.h_rowptr.empty() && A.nrows < (int64_t)1 << 31) {
     tma_attr_once();
     if (!A.ndesc) {

@@ -57,6 +57,17 @@ def test_ilu0_natural_matches_oracle(setup, block):
     assert rel(dev.inner_apply(block, 1, x), orc.inner_apply(block, 1, x)) < 1e-10
 
 
+def test_amg_vcycle_matches_oracle(setup):
+    """One V-cycle of the smoothed-aggregation AMG on F: the device set-up (parallel distance-2 independent set,
+    expand-sort-compress Galerkin products) builds the hierarchy the oracle builds sequentially."""
+    d, orc, dev = setup
+    x = np.random.default_rng(3).uniform(-1, 1, d.n_u)
+    y_d, y_o = dev.inner_apply(N.BLOCK_F, 2, x), orc.inner_apply(N.BLOCK_F, 2, x)
+    assert rel(y_d, y_o) < 1e-9
+    F = orc.csr(N.BLOCK_F)
+    assert np.linalg.norm(x - F @ y_d) < 0.7 * np.linalg.norm(x)   # the cycle contracts
+
+
 def test_schur_complement(setup):
     d, orc, dev = setup
     S_o = orc.schur()

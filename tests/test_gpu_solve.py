@@ -36,6 +36,9 @@ CASES = [
     (N.STATIONARY, 1, 0, N.MODE_NEWTON, "quad"),
     (N.STATIONARY, 0, 0, N.MODE_NEWTON, "tri"),      # GMRES
     (N.STATIONARY, 1, 2, N.MODE_NEWTON, "quad"),     # aSIMPLE, stationary flavour
+    (N.STATIONARY, 1, 1, N.MODE_STOKES, "quad"),     # blockTriangular, stationary flavour: AMG on F (configs 2, 4)
+    (N.STATIONARY, 0, 1, N.MODE_NEWTON, "tri"),
+    (N.STATIONARY, 2, 1, N.MODE_STOKES, "tri"),      # config 4's pairing: BiCGStab + blockTriangular
     (N.STATIONARY, 1, 2, N.MODE_STOKES, "tri"),
     (N.UNSTEADY, 1, 0, N.MODE_UNSTEADY_NEWTON, "tri"),
     (N.UNSTEADY, 1, 1, N.MODE_UNSTEADY_NEWTON, "tri"),
@@ -53,6 +56,11 @@ def test_solve_matches_oracle(flavour, solver, prec, mode, elem):
     rc_d, it_d, fr_d = dev.solve(flavour, solver, prec, tol, 2000)
     print(f"oracle: rc {rc_o} it {it_o} res {fr_o:.3e} inner {inner.tolist()} | gpu: rc {rc_d} it {it_d} res {fr_d:.3e} "
           f"inner [{dev.stat('INNER_F')}, {dev.stat('INNER_S')}, {dev.stat('PRECOND_APPLIES')}]")
+    if rc_o == N.NSX_E_NOCONV:
+        # BiCGStab with an inexact (inner-Krylov) preconditioner can stagnate: the reference would throw
+        # SolverControl::NoConvergence here, and so must the device path
+        assert rc_d == N.NSX_E_NOCONV and it_d == it_o
+        return
     assert rc_o == 0 and rc_d == 0
     x_o, x_d = orc.vec(2), dev.download(N.VEC_DELTA)
     assert np.linalg.norm(x_d - x_o) <= 1e-8 * np.linalg.norm(x_o)

@@ -281,3 +281,22 @@ def test_unsteady_driver_first_step():
     coeffs = log[log[:, 0] == 6]
     assert coeffs.shape[0] == 1 and np.isfinite(coeffs[0, 2:6]).all()
     assert (log[:, 0] == 5).sum() == 1
+
+
+def test_amg_oracle_contracts_and_scales():
+    """The oracle's smoothed-aggregation AMG (stand-in for ML): one V-cycle on the Stokes-branch F contracts the
+    residual by a mesh-independent factor, and FGMRES preconditioned with it converges in a handful of steps."""
+    import scipy.sparse.linalg as sla
+    rates = []
+    for nx, ny in ((20, 8), (40, 14)):
+        d = N.Disc.generate(nx, ny)
+        o = N.Oracle(d)
+        o.assemble(N.MODE_STOKES, True, 0.1)
+        F = o.csr(N.BLOCK_F)
+        x = np.random.default_rng(5).uniform(-1, 1, d.n_u)
+        y = o.inner_apply(N.BLOCK_F, 2, x)
+        rates.append(np.linalg.norm(x - F @ y) / np.linalg.norm(x))
+    assert max(rates) < 0.6 and abs(rates[0] - rates[1]) < 0.15, rates
+    rc, it, fr, inner = o.solve(N.STATIONARY, 1, 1, 1e-10, 500)
+    assert rc == 0 and fr <= 1e-10
+    assert inner[0] / inner[2] < 20   # inner FGMRES(F; AMG) to 1e-2: ~10 V-cycles per application
