@@ -107,8 +107,10 @@ def test_stationary_run_matches_oracle_driver(tmp_path):
     cl = _floats(r"Lift coefficient: ([0-9.e+-]+)", r.stdout)[-1]
     cd = _floats(r"Drag coefficient: ([0-9.e+-]+)", r.stdout)[-1]
     print("lift", cl, cl_o, "drag", cd, cd_o)
-    assert abs(cd - cd_o) <= 2e-6 * abs(cd_o)          # printed with 7 significant digits
-    assert abs(cl - cl_o) <= 2e-6 * max(abs(cl_o), 1e-3 * abs(cd_o))
+    # 1e-6 relative to the force on the cylinder (north_star); the lift of this symmetric set-up is ~1e-8 of the drag,
+    # i.e. at the level of the Krylov tolerance, and the coefficients are printed with 7 significant digits
+    scale = np.hypot(cd_o, cl_o)
+    assert abs(cd - cd_o) <= 2e-6 * scale and abs(cl - cl_o) <= 2e-6 * scale
     assert "Solving Stokes adding BCs" in r.stdout and "Solving NS" in r.stdout
     assert r.stdout.count("Computing drag and lift forces") > 0
 
@@ -132,7 +134,7 @@ def test_unsteady_run_matches_oracle_driver(tmp_path):
     print("Krylov iterations app   ", its_app)
     print("Krylov iterations oracle", its_orc)
     print("lift", cl, coeffs[2], "drag", cd, coeffs[3])
-    assert abs(cd - coeffs[3]) <= 2e-6 * abs(coeffs[3])
-    assert abs(cl - coeffs[2]) <= 2e-6 * max(abs(coeffs[2]), 1e-3 * abs(coeffs[3]))
+    scale = np.hypot(coeffs[2], coeffs[3])   # 1e-6 relative to the force on the cylinder (north_star)
+    assert abs(cd - coeffs[3]) <= 2e-6 * scale and abs(cl - coeffs[2]) <= 2e-6 * scale
     assert r.stdout.count("Debug ") == len(d.array("CYL_CELL"))     # one per cylinder face (NSSolver.cpp:883)
     assert "n =   1, t = 0.010000" in r.stdout
