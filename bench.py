@@ -111,12 +111,22 @@ def cpu_step_sample(disc, solver, prec, tol, nu, outer_cap, threads=None):
     return t_asm, t_solve, max(it, 1), int(orc().orc_get_threads())
 
 
+# outer FGMRES iterations of the full solve, measured on the B200 (bench_r1.json): the CPU sample runs a few outer
+# iterations and is scaled linearly to this count (early iterations are the cheap ones, so the scaling favours the CPU)
+MEASURED_OUTER = {("300,100", 1, 0): 814}
+
+
+def workload_name(args, nx, ny):
+    return (f"StationaryNSSolver -m {nx},{ny} -r 100 -s {args.solver} -t {args.tol:g} -p {args.prec}: first Newton step "
+            "(assemble + solve + update + line-search assembly)")
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  deal.II / Trilinos / MPI are
     not installable in this image, so the timed code is the oracle port of the reference path
-    (oracle/, OpenMP over the host cores).  Each step is a bounded sample: full assembly twice plus
-    the solve capped at --cpu-outer-cap outer iterations, extrapolated linearly in outer iterations
-    to the iteration count given by --cpu-outer-total (default: the cap, i.e. no extrapolation claim)."""
+    (oracle/, OpenMP over the host cores).  Each step is a bounded sample: both assemblies in full plus
+    the solve capped at --cpu-outer-cap outer iterations, scaled linearly in outer iterations to the count
+    the full solve needs (--cpu-outer-total, default: the count measured on the GPU for this configuration)."""
     from navier_stokes_solver_b200 import binding as B
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -126,20 +136,20 @@ def run_reference(args):
     nu = 1.0 / 10.0
     times = []
     cores = 1
+    total = args.cpu_outer_total or MEASURED_OUTER.get((args.mesh, args.solver, args.prec), 0)
     for s in range(args.warmup + args.steps):
         t_asm, t_solve, it, cores = cpu_step_sample(d, args.solver, args.prec, args.tol, nu, args.cpu_outer_cap)
-        total = args.cpu_outer_total or it
-        t = 2 * t_asm + t_solve * (total / it)
+        t = 2 * t_asm + t_solve * ((total or it) / it)
         if s >= args.warmup:
             times.append(t)
     val = float(np.mean(times))
+    sample = (f"oracle port on {cores} OpenMP threads: 2 full assemblies ({t_asm:.2f} s each) + solve capped at {it} outer iterations "
+              f"({t_solve:.2f} s), scaled linearly to {total or it} outer iterations")
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": val * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"StationaryNSSolver -m {nx},{ny} -r 100 -s {args.solver} -t {args.tol:g} -p {args.prec}: first Newton step",
-                       "cells": d.ncells, "dofs": d.n},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"2 full assemblies + solve capped at {args.cpu_outer_cap} outer iterations, scaled to {args.cpu_outer_total or 'the same'} outer iterations"},
+            "config": {"workload": workload_name(args, nx, ny), "cells": d.ncells, "dofs": d.n},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -163,6 +173,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    import ctypes
     import torch
     from navier_stokes_solver_b200 import binding as B
 
@@ -171,7 +182,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    if args.gpus != world:
+        raise SystemExit(f"--gpus {args.gpus} needs {args.gpus} ranks (python -m torch.distributed.run --nproc-per-node {args.gpus} ...), found WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -179,107 +193,166 @@ def main():
     nx, ny = parse_mesh(args.mesh)
     nu = 1.0 / 10.0   # first Reynolds stage of the continuation (NSSolverStationary.cpp:662-665)
     t0 = time.perf_counter()
-    d = B.Disc.generate(nx, ny)
-    dev = B.Device(d, device_id=local_rank, ordering=args.ordering)
+    # the reference's scheme: the cells are partitioned, every rank owns a contiguous row range of each block
+    g = B.Disc.generate(nx, ny, nranks=world)
+    stream = torch.cuda.Stream(device=local_rank)   # the library runs on this stream, so that torch events bracket its work
+    if world > 1:
+        d = g.local(rank)
+        ids = [B.Device.new_comm_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        dev = B.Device(d, device_id=local_rank, ordering=args.ordering, comm_id=ids[0], stream=ctypes.c_void_p(stream.cuda_stream))
+    else:
+        d = g
+        dev = B.Device(d, device_id=local_rank, ordering=args.ordering, stream=ctypes.c_void_p(stream.cuda_stream))
     setup_s = time.perf_counter() - t0
 
-    n = d.n
+    n = dev.n   # owned entries of this rank
     pinned_in = torch.zeros(2 * n, dtype=torch.float64).pin_memory()
     pinned_out = torch.zeros(n, dtype=torch.float64).pin_memory()
     stats = {}
 
-    def step(e2e):
-        if e2e:
-            dev.upload_ptr(B.VEC_SOLUTION, pinned_in.data_ptr())
-            dev.upload_ptr(B.VEC_DELTA, pinned_in.data_ptr() + 8 * n)
-        else:
-            dev.vec_set(B.VEC_SOLUTION, 0.0)
-            dev.vec_set(B.VEC_DELTA, 0.0)
+    def step(events=None):
+        """One Newton iteration through the C ABI with HOST buffers: state in, new solution out."""
+        if events:
+            events[0].record(stream)
+        dev.upload_ptr(B.VEC_SOLUTION, pinned_in.data_ptr())
+        dev.upload_ptr(B.VEC_DELTA, pinned_in.data_ptr() + 8 * n)
+        if events:
+            events[1].record(stream)
         r0 = dev.assemble(B.MODE_STOKES, True, nu)
         rc, it, fr = dev.solve(B.STATIONARY, args.solver, args.prec, args.tol, 20000)
         if rc != 0:
-            raise SystemExit(f"solve failed rc={rc} it={it} res={fr}")
+            raise SystemExit(f"solve failed rc={rc} it={it} res={fr}: {dev.last_error()}")
         dev.save_eval_point()
         dev.update(1.0)
         r1 = dev.assemble(B.MODE_STOKES, False, nu)
-        if e2e:
-            dev.download_ptr(B.VEC_SOLUTION, pinned_out.data_ptr())
+        if events:
+            events[2].record(stream)
+        dev.download_ptr(B.VEC_SOLUTION, pinned_out.data_ptr())
+        if events:
+            events[3].record(stream)
         stats.update(outer=it, inner_F=dev.stat("INNER_F"), inner_S=dev.stat("INNER_S"), applies=dev.stat("PRECOND_APPLIES"),
                      r0=r0, r1=r1, final_res=fr)
 
     def barrier():
         if world > 1:
-            import torch.distributed as dist
             dist.barrier()
         dev.synchronize()
         torch.cuda.synchronize()
 
-    def timed(e2e, steps):
-        barrier()
-        l0 = dev.stat("KERNEL_LAUNCHES")
-        t = time.perf_counter()
-        for _ in range(steps):
-            step(e2e)
-        barrier()
-        el = time.perf_counter() - t
-        if world > 1:
-            import torch.distributed as dist
-            tt = torch.tensor([el], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            el = float(tt.item())
-        return el, dev.stat("KERNEL_LAUNCHES") - l0
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        return float(tt.item())
 
     for _ in range(args.warmup):
-        step(False)
+        step()
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    el, launches = timed(False, args.steps)
-    el_e2e, _ = timed(True, args.steps)
-    # kernel timings (CUDA events on the library's stream, L2 flushed between launches)
+    if rank == 0:
+        sampler.start()
+    # timed region: K steps between barriers, CUDA events on the library's stream; the host<->device copies are
+    # bracketed by their own events so that the device-resident time (value) is the same steps minus the copies
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0 = dev.stat("KERNEL_LAUNCHES")
+    spmv0 = dev.stat("SPMV_CALLS")
+    t_wall = time.perf_counter()
+    e_begin.record(stream)
+    for k in range(args.steps):
+        step(evs[k])
+    e_end.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = dev.stat("KERNEL_LAUNCHES") - l0
+    spmv_calls = dev.stat("SPMV_CALLS") - spmv0
+    total_ms = e_begin.elapsed_time(e_end)
+    copy_ms = sum(e[0].elapsed_time(e[1]) + e[2].elapsed_time(e[3]) for e in evs)
+    e2e_s = max_over_ranks(total_ms) / 1e3 / args.steps
+    value = max_over_ranks(total_ms - copy_ms) / 1e3 / args.steps
+    wall_s = max_over_ranks(t_wall) / args.steps
+    launches_all = int(sum_over_ranks(float(launches)))
+    h2d = int(sum_over_ranks(16.0 * n))
+    d2h = int(sum_over_ranks(8.0 * n + 16))
+
+    # kernel timings (CUDA events on the library's stream, L2 flushed between launches); rank 0's share at N > 1
     reps = args.kernel_reps
     rng = np.random.default_rng(42)
     dev.upload(B.VEC_TMP0, rng.uniform(-1, 1, n))
     dev.set_time_params(B.MODE_NEWTON, 1.0 / 90.0)
-    dev.upload(B.VEC_SOLUTION, B.synthetic_state(d, 1234))
-    for w in (0, 1, 2, 3, 4):
+    gstate = B.synthetic_state(g, 1234)
+    dev.upload(B.VEC_SOLUTION, d.scatter_owned(gstate, g.n_u) if world > 1 else gstate)
+    names = [("block_spmv", 0), ("spmv_F", 1), ("assembly_newton", 2), ("dot", 3), ("axpy", 4), ("sgs_F", 5), ("ilu_apply_F", 6), ("ilu_factor_F", 7)]
+    if world > 1:
+        names = [x for x in names if x[1] in (2, 3, 4, 5, 6, 7)] + [("block_spmv", 0), ("spmv_F", 1)]   # collective ones last, all ranks alike
+    for _, w in names:
         dev.time_kernel(w, 5, True)
-    k_ms = {name: dev.time_kernel(w, reps, True) for name, w in
-            (("block_spmv", 0), ("spmv_F", 1), ("assembly_newton", 2), ("dot", 3), ("axpy", 4), ("sgs_F", 5), ("ilu_apply_F", 6), ("ilu_factor_F", 7))}
-    clocks = sampler.stop()
+    k_ms = {name: dev.time_kernel(w, reps, True) for name, w in names}
+    clocks = sampler.stop() if rank == 0 else None
 
     nnz = {b: dev.nnz(b) for b in (B.BLOCK_F, B.BLOCK_BT, B.BLOCK_B, B.BLOCK_MP)}
     nnz_j = nnz[B.BLOCK_F] + nnz[B.BLOCK_BT] + nnz[B.BLOCK_B]
     peak, peak_kind = load_peaks()
+    n_u_own, ncells_own = dev.n_u, d.ncells
     bts = spmv_bytes(nnz_j, n)
-    achieved = bts / (k_ms["block_spmv"] * 1e-3) / 1e9
-    asm_bytes = 8 * (nnz_j + nnz[B.BLOCK_MP]) + 16 * n + d.ncells * (64 + 4 * 41)
+    spmv_gbs = bts / (k_ms["block_spmv"] * 1e-3) / 1e9
+    spmv_f_bytes = 12 * nnz[B.BLOCK_F] + 20 * n_u_own
+    # one SGS application = a lower and an upper sweep over the rank-local block: every value + column once, row pointers,
+    # x in, intermediate out + in, y out (DESIGN.md section 4)
+    sgs_bytes = 12 * nnz[B.BLOCK_F] + 8 * (n_u_own + 1) + 32 * n_u_own
+    sgs_gbs = sgs_bytes / (k_ms["sgs_F"] * 1e-3) / 1e9
+    asm_bytes = 8 * (nnz_j + nnz[B.BLOCK_MP]) + 16 * n + ncells_own * (64 + 4 * 41)
     kernels = {
-        "block_spmv": {"ms": k_ms["block_spmv"], "GBps": achieved, "frac_hbm": achieved / peak},
-        "spmv_F": {"ms": k_ms["spmv_F"], "GBps": (12 * nnz[B.BLOCK_F] + 20 * d.n_u) / (k_ms["spmv_F"] * 1e-3) / 1e9},
-        "assembly_newton": {"ms": k_ms["assembly_newton"], "GFLOPs_fp64": 1.206e5 * d.ncells / (k_ms["assembly_newton"] * 1e-3) / 1e9,
+        "block_spmv": {"ms": k_ms["block_spmv"], "GBps": spmv_gbs, "frac_hbm": spmv_gbs / peak, "algorithmic_bytes": bts},
+        "spmv_F": {"ms": k_ms["spmv_F"], "GBps": spmv_f_bytes / (k_ms["spmv_F"] * 1e-3) / 1e9,
+                   "frac_hbm": spmv_f_bytes / (k_ms["spmv_F"] * 1e-3) / 1e9 / peak},
+        "assembly_newton": {"ms": k_ms["assembly_newton"], "GFLOPs_fp64": 1.206e5 * ncells_own / (k_ms["assembly_newton"] * 1e-3) / 1e9,
                             "GBps_min_bytes": asm_bytes / (k_ms["assembly_newton"] * 1e-3) / 1e9},
         "dot": {"ms": k_ms["dot"], "GBps": 16 * n / (k_ms["dot"] * 1e-3) / 1e9},
         "axpy": {"ms": k_ms["axpy"], "GBps": 24 * n / (k_ms["axpy"] * 1e-3) / 1e9},
-        "sgs_F": {"ms": k_ms["sgs_F"], "levels": dev.stat("LEVELS_F")},
+        "sgs_F": {"ms": k_ms["sgs_F"], "levels": dev.stat("LEVELS_F"), "GBps": sgs_gbs, "frac_hbm": sgs_gbs / peak, "algorithmic_bytes": sgs_bytes},
         "ilu_apply_F": {"ms": k_ms["ilu_apply_F"]},
         "ilu_factor_F": {"ms": k_ms["ilu_factor_F"]},
     }
-    value = el / args.steps
+    # share of the step spent in the two candidates for "dominant kernel" (launch counts x launch time)
+    inner_f = stats["inner_F"]
+    share = {"sgs_F": inner_f * k_ms["sgs_F"] * 1e-3 / value if args.prec == 0 else 0.0,
+             "spmv_F": inner_f * k_ms["spmv_F"] * 1e-3 / value,
+             "block_spmv": stats["outer"] * k_ms["block_spmv"] * 1e-3 / value}
+    for k, v in share.items():
+        kernels[k]["est_share_of_step"] = v
+    dom = max(share, key=share.get)
+    dom_kernel = {"sgs_F": "k_sweep_coop<SGS> (symmetric Gauss-Seidel sweeps on F, inner preconditioner)",
+                  "spmv_F": "k_spmv_tma (F SpMV of the inner FGMRES)", "block_spmv": "k_spmv_tma (Jacobian block SpMV)"}[dom]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"StationaryNSSolver -m {nx},{ny} -r 100 -s {args.solver} -t {args.tol:g} -p {args.prec}: first Newton step "
-                               "(assemble + solve + update + line-search assembly)",
-                   "cells": d.ncells, "dofs": n, "nnz_J": nnz_j, "elimination_order": "multicolour" if args.ordering else "natural",
+        "config": {"workload": workload_name(args, nx, ny), "cells": g.ncells, "dofs": g.n, "nnz_J_rank0": nnz_j,
+                   "partition": f"{world} strips of cells, owned rows per rank (rank 0: {n} dofs)" if world > 1 else "one rank",
+                   "elimination_order": "multicolour" if args.ordering else "natural",
                    "outer_iterations": stats["outer"], "inner_F_iterations": stats["inner_F"], "inner_Mp_or_S_iterations": stats["inner_S"],
-                   "final_residual": stats["final_res"], "l2_policy": "kernel timings flush L2 (256 MiB memset) between launches; step working set 0.5 GB > L2",
-                   "setup_s": setup_s},
-        "e2e": {"value": el_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n + 16},
-        "gpu_launches": launches,
+                   "final_residual": stats["final_res"],
+                   "l2_policy": "kernel timings flush L2 (512 MiB memset) between launches; the step's working set (0.5 GB matrix + 60 Krylov vectors) exceeds L2",
+                   "setup_s": setup_s, "wall_s_per_step": wall_s},
+        "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches_all,
+        "spmv_launches_rank0": spmv_calls,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_block_spmv (Jacobian block SpMV)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes": bts},
+        "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                     "frac": kernels[dom]["GBps"] / peak, "traffic": None, "peak_kind": peak_kind,
+                     "algorithmic_bytes": kernels[dom].get("algorithmic_bytes", spmv_f_bytes), "est_share_of_step": share[dom]},
+        "spmv_roofline": {"kernel": "k_spmv_tma (Jacobian block SpMV)", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
+                          "algorithmic_bytes": bts},
         "kernels": kernels,
     }
     if rank == 0 and not args.no_cpu and world == 1:
@@ -290,8 +363,8 @@ def main():
                                           f"iterations ({t_solve:.2f} s), scaled to the GPU run's {stats['outer']} outer iterations"}
     if rank == 0:
         print(json.dumps(line))
+    dev.close()
     if world > 1:
-        import torch.distributed as dist
         dist.destroy_process_group()
 
 

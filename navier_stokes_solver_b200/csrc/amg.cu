@@ -552,6 +552,8 @@ void vcycle(Ctx &c, AmgHierarchy &H, size_t lev, double *x, const double *b) {
 void amg_setup(Ctx &c, const DevCSR &F) {
   if (!c.amg) c.amg = std::shared_ptr<AmgHierarchy>(new AmgHierarchy, [](AmgHierarchy *p) { delete p; });
   AmgHierarchy &H = *c.amg;
+  // everything below works on this rank's diagonal block: its dot products must not be summed over the ranks
+  struct LocalScope { Ctx &c; void *comm; explicit LocalScope(Ctx &cc) : c(cc), comm(cc.comm) { c.comm = nullptr; } ~LocalScope() { c.comm = comm; } } local_scope(c);
   H.L.clear();
   H.L.emplace_back(new AmgLevel);
   {

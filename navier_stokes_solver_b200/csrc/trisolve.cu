@@ -274,7 +274,7 @@ TriPlan &tri_plan(Ctx &c, int block) {
   auto it = c.tri.find(block);
   if (it != c.tri.end() && it->second->ordering == c.ordering) return *it->second;
   const DevCSR &A = block_ref(c, block);
-  if (A.nrows != A.ncols) throw std::invalid_argument("triangular plan needs a square block");
+  if (A.nrows > A.ncols) throw std::invalid_argument("triangular plan needs a square block (owned rows x owned + ghost columns on a partitioned system)");
   if (A.h_rowptr.empty()) throw std::logic_error("block pattern is not set");
   const std::vector<int64_t> &owned = (block == NSX_BLOCK_F) ? c.owned_u : c.owned_p;
   std::unique_ptr<TriPlan> up(new TriPlan);
