@@ -39,7 +39,7 @@ enum nsx_option {
   NSX_OPT_ORDERING = 0,   /* elimination order of ILU(0)/SGS: 0 natural (as Ifpack), 1 multicolour (default) */
   NSX_OPT_VERBOSE = 1,
   NSX_OPT_ORTHO = 2,      /* Gram-Schmidt of GMRES/FGMRES: 0 modified chain (as deal.II), 1 batched classical, two passes (default) */
-  NSX_OPT_COOP_SWEEP = 3, /* multicolour sweeps as one cooperative launch (default 1) */
+  NSX_OPT_COOP_SWEEP = 3, /* ILU/SGS sweeps: 1 colour-phased persistent kernel with its own grid barrier (default, multicolour order), 2 level-phased cooperative launch, 0 one launch per level */
   NSX_OPT_STREAM_SPMV = 4 /* SpMV kernel: 2 TMA-fed persistent (default), 1 streaming with plain loads, 0 sub-warp per row */
 };
 enum nsx_stat {

@@ -122,7 +122,9 @@ int nsx_set_option(nsx_ctx *ctx, int option, int64_t value) {
         ctx->ordering = (int)value; break;
       case NSX_OPT_VERBOSE: ctx->verbose = (int)value; break;
       case NSX_OPT_ORTHO: ctx->ortho = value ? 1 : 0; break;
-      case NSX_OPT_COOP_SWEEP: ctx->coop_sweep = value ? 1 : 0; break;
+      case NSX_OPT_COOP_SWEEP:
+        if (value < 0 || value > 2) throw std::invalid_argument("sweep kernel must be 0 (a launch per level), 1 (colour-phased persistent) or 2 (level-phased cooperative)");
+        ctx->coop_sweep = (int)value; break;
       case NSX_OPT_STREAM_SPMV:
         if (value < 0 || value > 3) throw std::invalid_argument("SpMV kernel must be 0, 1, 2 or 3");
         ctx->stream_spmv = (int)value; break;

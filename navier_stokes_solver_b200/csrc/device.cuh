@@ -106,6 +106,12 @@ struct TriPlan {
   DevBuf<double> work, yp;              // intermediate vectors (permuted numbering)
   bool factored = false;
   int coop_grid = 0;                    // grid of the cooperative sweep (0: not sized yet)
+  // colour-phased persistent sweep (multicolour order): rows of a colour are contiguous in the permuted numbering
+  std::vector<int64_t> cptr;            // colour pointers (empty for the natural order)
+  DevBuf<int64_t> d_cptr;
+  DevBuf<int4> rinfo;                   // per row: start of the row in the plan (2 x int32 = int64), lower count, upper count
+  DevBuf<unsigned long long> barrier;   // arrival counter of the in-kernel grid barrier (monotonic across launches)
+  unsigned long long barrier_epoch = 0;
   std::vector<int64_t> h_rowptr, lvl_f, lvl_b;
   std::vector<int32_t> h_col, h_diag, h_perm;
   std::vector<TriStep> steps_f, steps_b;
@@ -135,7 +141,7 @@ struct Ctx {
   int ndesc_u = 0, ndesc_p = 0;
   DevBuf<int32_t> rb_u, rb_p;  // row blocks of the Jacobian block SpMV: velocity rows (F + Bt), pressure rows (B)
   int nrb_u = 0, nrb_p = 0;
-  int coop_sweep = 1;   // multicolour sweeps as one cooperative launch with grid barriers between colours
+  int coop_sweep = 1;   // multicolour sweeps as one cooperative launch with grid barriers between colours (2: the older level-phased kernel)
   int num_sms = 148;
 
   // discretisation

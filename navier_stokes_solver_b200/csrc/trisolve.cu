@@ -209,6 +209,175 @@ __global__ void __launch_bounds__(256) k_sweep_coop(TriArgs A, const int32_t *__
   }
 }
 
+// ---- colour-phased persistent sweep ------------------------------------------------------------------------
+// One CTA of FTHREADS threads per SM, a sub-warp of FT lanes per row, 2 x ncol phases (colours ascending for the lower
+// sweep, descending for the upper one) separated by a hand-rolled split grid barrier (one arrival counter in L2:
+// fence + red by one thread per CTA, ld.acquire spin; ~1.4 us measured on B200, tools/microbench/grid_barrier.cu).
+// A phase on the critical path is: barrier -> gather of the work vector through L2 -> shuffle reduction -> store.
+// Everything that does not depend on the previous colour is fetched ahead of the barrier wait: each lane stages the
+// values and columns of its share of the NEXT phase's row in shared memory with cp.async (FCAP entries per lane, i.e.
+// rows of up to FCAP x FT entries per triangle -- every row of the Q3/Q2 and P2/P1 patterns -- at no register cost),
+// the row's diagonal and right-hand side ride in registers, and the row descriptor + permutation entry are loaded two
+// phases ahead.  No DRAM round trip is left between two barriers.
+constexpr int FT = 4, FCAP = 24;
+
+__device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
+struct RowPreF {
+  int32_t row, prm, cnt;   // cnt: staged entries of this lane
+  int64_t rest_b, rest_e;  // entries beyond the staged ones (none on the supported element patterns)
+  double dg, xin;
+};
+
+// split grid barrier: arrive (after the CTA's stores) ... independent loads of the next phase ... wait.  The fence of the
+// arriving thread must not sit behind the prefetch loads (it would wait for their DRAM round trip), so they are issued
+// between the two halves and their latency overlaps the wait.
+__device__ __forceinline__ void grid_arrive(unsigned long long *counter) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1ull);
+  }
+}
+__device__ __forceinline__ void grid_wait(unsigned long long *counter, unsigned long long target) {
+  if (threadIdx.x == 0) {
+    unsigned long long v;
+    do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory"); } while (v < target);
+  }
+  __syncthreads();
+}
+
+// sv / sc: this thread's column of the staging area, stride = blockDim.x entries
+template <bool FWD, int FTHREADS>
+__device__ __forceinline__ void stage_row(const TriArgs &A, int32_t row, int4 ri, int32_t prm, int lane, double *sv, int32_t *sc, RowPreF &P) {
+  P.row = row; P.prm = prm; P.cnt = 0;
+  if (row < 0) return;
+  const int64_t b = ((int64_t)(uint32_t)ri.x) | ((int64_t)ri.y << 32), d = b + ri.z;
+  const int64_t lo = FWD ? b : d + 1, hi = FWD ? d : d + 1 + ri.w;
+  int cnt = 0;
+  for (int64_t k = lo + lane; k < hi && cnt < FCAP; k += FT, ++cnt) {
+    cp_async_8(sv + cnt * FTHREADS, A.val + k);
+    cp_async_4(sc + cnt * FTHREADS, A.col + k);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  P.cnt = cnt;
+  P.rest_b = lo + lane + (int64_t)FCAP * FT; P.rest_e = hi;
+  P.dg = __ldcs(A.val + d);
+  P.xin = FWD ? __ldg(A.x + prm) : 0.0;
+}
+
+template <bool SGS, bool FWD, int FTHREADS>
+__device__ __forceinline__ void finish_row_f(const TriArgs &A, const RowPreF &P, const double *sv, const int32_t *sc, const cg::thread_block_tile<FT> &tile) {
+  if (P.row < 0) return;  // uniform over the tile
+  const double *src = FWD ? A.w : A.yp;
+  double s0 = 0, s1 = 0;
+  int t = 0;
+  for (; t + 1 < P.cnt; t += 2) {
+    s0 += sv[t * FTHREADS] * __ldcg(src + sc[t * FTHREADS]);
+    s1 += sv[(t + 1) * FTHREADS] * __ldcg(src + sc[(t + 1) * FTHREADS]);
+  }
+  if (t < P.cnt) s0 += sv[t * FTHREADS] * __ldcg(src + sc[t * FTHREADS]);
+  for (int64_t k = P.rest_b; k < P.rest_e; k += FT) s1 += __ldcs(A.val + k) * __ldcg(src + __ldcs(A.col + k));
+  double s = s0 + s1;
+#pragma unroll
+  for (int o = FT / 2; o > 0; o >>= 1) s += tile.shfl_down(s, o);
+  if (tile.thread_rank() == 0) {
+    if (FWD) {
+      const double r = P.xin - s;
+      A.w[P.row] = SGS ? r / P.dg : r;
+    } else {
+      const double wv = __ldcg(A.w + P.row);
+      const double r = SGS ? wv - s / P.dg : (wv - s) / P.dg;
+      A.yp[P.row] = r;
+      A.y[P.prm] = r;
+    }
+  }
+}
+
+template <bool SGS, int FTHREADS>
+__global__ void __launch_bounds__(FTHREADS, 1) k_sweep_phased(TriArgs A, const int4 *__restrict__ rinfo, const int64_t *__restrict__ cptr, int ncol,
+                                                               unsigned long long *counter, unsigned long long epoch0) {
+  extern __shared__ __align__(16) unsigned char stage_raw[];
+  __shared__ int64_t s_cptr[258];
+  double *sv = reinterpret_cast<double *>(stage_raw) + threadIdx.x;                                   // [FCAP][FTHREADS] doubles
+  int32_t *sc = reinterpret_cast<int32_t *>(stage_raw + (size_t)FCAP * FTHREADS * sizeof(double)) + threadIdx.x;  // [FCAP][FTHREADS] ints
+  for (int i = threadIdx.x; i <= ncol; i += FTHREADS) s_cptr[i] = cptr[i];
+  __syncthreads();
+  auto tile = cg::tiled_partition<FT>(cg::this_thread_block());
+  const int lane = tile.thread_rank();
+  const int64_t sub = (blockIdx.x * (int64_t)FTHREADS + threadIdx.x) / FT, nsub = (int64_t)gridDim.x * FTHREADS / FT;
+  const int nph = 2 * ncol;
+  unsigned long long target = epoch0;
+  // row of this sub-warp in phase p (-1: none)
+  auto row_of = [&](int p) -> int32_t {
+    if (p >= nph) return -1;
+    const int col = p < ncol ? p : nph - 1 - p;
+    const int64_t r = s_cptr[col] + sub;
+    return r < s_cptr[col + 1] ? (int32_t)r : -1;
+  };
+  RowPreF P;
+  // ring of row descriptors, three phases deep: slot (p % 3) holds the descriptor + permutation entry of this sub-warp's row in phase p
+  constexpr int NSUB = FTHREADS / FT;
+  __shared__ __align__(16) int4 s_ri[3 * NSUB];
+  __shared__ int32_t s_prm[3 * NSUB];
+  const int lsub = threadIdx.x / FT;
+  int32_t row1 = row_of(1);
+  int4 ri1 = make_int4(0, 0, 0, 0);
+  int32_t prm1 = 0;
+  {
+    const int32_t row0 = row_of(0);
+    int4 ri0 = make_int4(0, 0, 0, 0);
+    int32_t prm0 = 0;
+    if (row0 >= 0) { ri0 = __ldg(rinfo + row0); prm0 = __ldg(A.perm + row0); }
+    if (row1 >= 0) { ri1 = __ldg(rinfo + row1); prm1 = __ldg(A.perm + row1); }
+    stage_row<true, FTHREADS>(A, row0, ri0, prm0, lane, sv, sc, P);
+    asm volatile("cp.async.commit_group;" ::: "memory");  // (empty) descriptor group, keeps the group count per phase uniform
+    // descriptor of phase 1 into its ring slot
+    if (row1 >= 0 && lane == 0) { s_ri[(1 % 3) * NSUB + lsub] = ri1; s_prm[(1 % 3) * NSUB + lsub] = prm1; }
+  }
+  __syncthreads();
+  for (int p = 0; p < nph; ++p) {
+    const bool fwd = p < ncol;
+    const int col = fwd ? p : nph - 1 - p;
+    // the staged row of this phase: its group is the last but one (the descriptor group of phase p + 2 follows it)
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    if (fwd) finish_row_f<SGS, true, FTHREADS>(A, P, sv, sc, tile); else finish_row_f<SGS, false, FTHREADS>(A, P, sv, sc, tile);
+    // colours wider than the grid: the remaining rows, staged and consumed on the spot
+    for (int64_t r = s_cptr[col] + sub + nsub; r < s_cptr[col + 1]; r += nsub) {
+      RowPreF Q;
+      const int4 ri = __ldg(rinfo + r);
+      const int32_t prm = __ldg(A.perm + r);
+      if (fwd) stage_row<true, FTHREADS>(A, (int32_t)r, ri, prm, lane, sv, sc, Q); else stage_row<false, FTHREADS>(A, (int32_t)r, ri, prm, lane, sv, sc, Q);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (fwd) finish_row_f<SGS, true, FTHREADS>(A, Q, sv, sc, tile); else finish_row_f<SGS, false, FTHREADS>(A, Q, sv, sc, tile);
+    }
+    if (p + 1 < nph) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");   // descriptor of phase p + 1 (issued a phase ago) has landed
+      grid_arrive(counter);                                    // ... and its __syncthreads publishes it to the sub-warp
+      // next phase's matrix entries from the descriptor in the ring, then the descriptor of the phase after it (no register
+      // ever depends on that load before the next barrier has passed)
+      const int32_t rown = row_of(p + 1);
+      int4 ri = make_int4(0, 0, 0, 0);
+      int32_t prm = 0;
+      if (rown >= 0) { ri = s_ri[((p + 1) % 3) * NSUB + lsub]; prm = s_prm[((p + 1) % 3) * NSUB + lsub]; }
+      if (p + 1 < ncol) stage_row<true, FTHREADS>(A, rown, ri, prm, lane, sv, sc, P); else stage_row<false, FTHREADS>(A, rown, ri, prm, lane, sv, sc, P);
+      const int32_t row2 = row_of(p + 2);
+      if (row2 >= 0 && lane == 0) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(s_ri + ((p + 2) % 3) * NSUB + lsub)), "l"(rinfo + row2) : "memory");
+        cp_async_4(s_prm + ((p + 2) % 3) * NSUB + lsub, A.perm + row2);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      target += gridDim.x;
+      grid_wait(counter, target);
+    }
+  }
+}
+
 __global__ void k_gather_values(int64_t nnz, const int64_t *__restrict__ src, const double *__restrict__ a, double *__restrict__ v) {
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) v[k] = a[src[k]];
 }
@@ -309,6 +478,29 @@ TriPlan &tri_plan(Ctx &c, int block) {
     for (int64_t i = 0; i < n; ++i) cnt[colour[i] + 1]++;
     for (int q = 0; q < ncol; ++q) cnt[q + 1] += cnt[q];
     for (int64_t i = 0; i < n; ++i) perm[cnt[colour[i]]++] = (int32_t)i;
+    // Greedy colouring may use more colours than the elimination order needs phases.  Re-sort the rows by their
+    // dependency level under the colour order: two coupled rows keep their relative order (the later one sits at least
+    // one level higher), so the triangular split -- and with it the preconditioner -- is unchanged, while the number of
+    // phases drops to the depth of the dependency graph and every level is a contiguous row range for both sweeps.
+    for (int64_t r = 0; r < n; ++r) iperm[perm[r]] = (int32_t)r;
+    std::vector<int32_t> level(n, 0);
+    int nlev = 0;
+    for (int64_t r = 0; r < n; ++r) {
+      const int64_t i = perm[r];
+      int32_t m = 0;
+      for (int64_t k = A.h_rowptr[i]; k < A.h_rowptr[i + 1]; ++k) {
+        const int32_t j = A.h_col[k];
+        if (j != i && range[j] == range[i] && iperm[j] < r) m = std::max(m, level[iperm[j]] + 1);
+      }
+      level[r] = m; nlev = std::max(nlev, m + 1);
+    }
+    std::vector<int64_t> lp(nlev + 1, 0);
+    for (int64_t r = 0; r < n; ++r) lp[level[r] + 1]++;
+    for (int q = 0; q < nlev; ++q) lp[q + 1] += lp[q];
+    P.cptr = lp;
+    std::vector<int32_t> perm2(n);
+    for (int64_t r = 0; r < n; ++r) perm2[lp[level[r]]++] = perm[r];
+    perm.swap(perm2);
   }
   for (int64_t r = 0; r < n; ++r) iperm[perm[r]] = (int32_t)r;
   // permuted, filtered pattern
@@ -357,6 +549,18 @@ TriPlan &tri_plan(Ctx &c, int block) {
   P.order_bwd.upload(ob, c.stream);
   P.d_lvl_f.upload(P.lvl_f, c.stream);
   P.d_lvl_b.upload(P.lvl_b, c.stream);
+  if (!P.cptr.empty()) {
+    std::vector<int4> ri(n);
+    for (int64_t r = 0; r < n; ++r) {
+      const int64_t b = P.h_rowptr[r];
+      ri[r] = make_int4((int)(b & 0xffffffffll), (int)(b >> 32), P.h_diag[r], (int)(P.h_rowptr[r + 1] - b) - P.h_diag[r] - 1);
+    }
+    P.rinfo.upload(ri, c.stream);
+    P.d_cptr.upload(P.cptr, c.stream);
+    P.barrier.alloc(1);
+    P.barrier.zero(c.stream);
+    P.barrier_epoch = 0;
+  }
   P.val.alloc(P.nnz);
   P.work.alloc(n);
   P.yp.alloc(n);
@@ -399,6 +603,28 @@ template <bool SGS>
 static void sweep(Ctx &c, TriPlan &P, double *y, const double *x) {
   TriArgs T = args_of(P, x, y);
   const int nlf = (int)P.lvl_f.size() - 1, nlb = (int)P.lvl_b.size() - 1;
+  if (c.coop_sweep == 1 && !P.cptr.empty() && P.cptr.size() <= 257) {
+    const int ncol = (int)P.cptr.size() - 1;
+    const int4 *ri = P.rinfo.p;
+    const int64_t *cp = P.d_cptr.p;
+    unsigned long long *counter = P.barrier.p, epoch0 = P.barrier_epoch;
+    int a_ncol = ncol;
+    void *args[] = {&T, &ri, &cp, &a_ncol, &counter, &epoch0};
+    static const int threads = [] { const char *e = getenv("NSX_SWEEP_THREADS"); return e ? atoi(e) : 512; }();
+    const void *fn = threads == 256 ? (const void *)k_sweep_phased<SGS, 256> : threads == 384 ? (const void *)k_sweep_phased<SGS, 384>
+                     : threads == 768 ? (const void *)k_sweep_phased<SGS, 768> : (const void *)k_sweep_phased<SGS, 512>;
+    const int nthreads = (threads == 256 || threads == 384 || threads == 768) ? threads : 512;
+    const size_t smem = (size_t)FCAP * nthreads * (sizeof(double) + sizeof(int32_t));
+    static std::vector<const void *> attr_done;  // kernels whose dynamic shared memory limit has been raised
+    if (std::find(attr_done.begin(), attr_done.end(), fn) == attr_done.end()) {
+      NSX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_done.push_back(fn);
+    }
+    NSX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(c.num_sms), dim3(nthreads), args, smem, c.stream));
+    P.barrier_epoch += (unsigned long long)(2 * ncol - 1) * (unsigned long long)c.num_sms;
+    c.stat_launches++;
+    return;
+  }
   if (c.coop_sweep && nlf + nlb <= 512) {
     if (!P.coop_grid) {
       int per_sm = 0;

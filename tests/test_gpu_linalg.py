@@ -142,8 +142,16 @@ def test_cooperative_sweep_equals_level_launches(setup, kind):
     try:
         dev.set_option(N.OPT_COOP_SWEEP, 0)
         y0 = dev.inner_apply(N.BLOCK_F, kind, x)
+        dev.set_option(N.OPT_COOP_SWEEP, 2)
+        y2 = dev.inner_apply(N.BLOCK_F, kind, x)
+        np.testing.assert_array_equal(y0, y2)
+        # the colour-phased persistent kernel sums a row over 4 lanes instead of 8: same values up to summation order,
+        # and the same bits from one application to the next
         dev.set_option(N.OPT_COOP_SWEEP, 1)
         y1 = dev.inner_apply(N.BLOCK_F, kind, x)
-        np.testing.assert_array_equal(y0, y1)
+        assert rel(y1, y0) < 1e-13
+        for _ in range(5):
+            np.testing.assert_array_equal(dev.inner_apply(N.BLOCK_F, kind, x), y1)
     finally:
         dev.set_option(N.OPT_ORDERING, 0)
+        dev.set_option(N.OPT_COOP_SWEEP, 1)
