@@ -147,6 +147,8 @@ int nsx_precond_apply(nsx_ctx *ctx, int flavour, int prec, double alpha, int vec
  * what: 0 Jacobian block SpMV, 1 F SpMV, 2 assembly (matrix + rhs kernels), 3 dot, 4 axpy, 5 SGS(F) apply,
  * 6 ILU(F) apply, 7 ILU(F) factorisation.  nsx_set_time_params picks the assembly branch that `what` = 2 times. */
 int nsx_set_time_params(nsx_ctx *ctx, int mode, double nu, double dt);
+/* flush_l2: 1 = L2 flushed before every launch, one event pair per launch; 0 = no flush; 2 = `reps` launches back to back inside one
+ * event pair (for kernels whose input is larger than L2: no launch / event overhead in the figure). */
 int nsx_time_kernel(nsx_ctx *ctx, int what, int reps, int flush_l2, double *ms_per_launch);
 int nsx_synchronize(nsx_ctx *ctx);
 /* elimination order used for a block's ILU/SGS (new -> old), for oracle parity */
