@@ -40,7 +40,7 @@ enum nsx_option {
   NSX_OPT_VERBOSE = 1,
   NSX_OPT_ORTHO = 2,      /* Gram-Schmidt of GMRES/FGMRES: 0 modified chain (as deal.II), 1 batched classical, two passes (default) */
   NSX_OPT_COOP_SWEEP = 3, /* ILU/SGS sweeps: 1 colour-phased persistent kernel with its own grid barrier (default, multicolour order), 2 level-phased cooperative launch, 0 one launch per level */
-  NSX_OPT_STREAM_SPMV = 4 /* SpMV kernel: 2 TMA-fed persistent (default), 1 streaming with plain loads, 0 sub-warp per row */
+  NSX_OPT_STREAM_SPMV = 4 /* SpMV kernel: 3 TMA-fed persistent, rows reduced from the stage, paired velocity columns (default); 2 TMA-fed, products staged; 1 streaming with plain loads; 0 sub-warp per row */
 };
 enum nsx_stat {
   NSX_STAT_INNER_F = 0, NSX_STAT_INNER_S = 1, NSX_STAT_PRECOND_APPLIES = 2, NSX_STAT_KERNEL_LAUNCHES = 3,

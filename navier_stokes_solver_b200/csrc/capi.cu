@@ -49,6 +49,7 @@ void set_block(Ctx &c, DevCSR &A, int64_t nrows, int64_t ncols, const int64_t *r
   NSX_CUDA(cudaMemcpyAsync(A.col.p, dev_col, A.nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
   A.val.alloc_padded(A.nnz, 16, c.stream);  // val[nnz + 12] is the sink of the ghost rows' contributions (assemble.cu)
   A.nrb = A.ndesc = 0;
+  A.pair_state = 0; A.pcol.release();
   c.nrb_u = c.nrb_p = c.ndesc_u = c.ndesc_p = 0;
   A.max_row = 0;
   for (int64_t i = 0; i < nrows; ++i) {

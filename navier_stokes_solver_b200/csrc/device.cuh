@@ -78,6 +78,8 @@ struct DevCSR {
   DevBuf<int32_t> col;
   DevBuf<double> val;
   DevBuf<int32_t> diag;  // offset of the diagonal inside each row (square blocks), -1 if absent
+  DevBuf<int32_t> pcol;       // paired columns (kernels_spmv.cu build_pairs), when the block's columns pair up
+  int pair_state = 0;         // 0 not examined, 1 paired, -1 does not pair
   DevBuf<RowBlockDesc> desc;  // row blocks of the TMA-fed SpMV
   int ndesc = 0;
   DevBuf<int32_t> rb;   // row blocks of the streaming SpMV (runs of rows with a bounded non-zero count)
@@ -136,7 +138,7 @@ struct Ctx {
   int verbose = 0;
   int ordering = 1;
   int ortho = 1;        // 0 modified Gram-Schmidt chain (as deal.II), 1 batched classical Gram-Schmidt with re-orthogonalisation
-  int stream_spmv = 2;  // 2: TMA-fed persistent SpMV, 1: streaming through shared memory with plain loads, 0: sub-warp per row
+  int stream_spmv = 3;  // 3: TMA-fed persistent SpMV, rows reduced straight from the stage, paired columns (default); 2: same ring, products staged in shared memory; 1: streaming with plain loads; 0: sub-warp per row
   DevBuf<RowBlockDesc> desc_u, desc_p;
   int ndesc_u = 0, ndesc_p = 0;
   DevBuf<int32_t> rb_u, rb_p;  // row blocks of the Jacobian block SpMV: velocity rows (F + Bt), pressure rows (B)

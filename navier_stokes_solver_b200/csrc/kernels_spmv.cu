@@ -99,6 +99,7 @@ struct StreamMat {
   const int32_t *col;
   const double *val;
   const double *x;
+  const int32_t *pcol = nullptr;  // paired columns (one even column id per two adjacent non-zeros), or null
 };
 
 __device__ __forceinline__ void stream_rows(const int32_t *__restrict__ rb, int b, const StreamMat &A1, const StreamMat &A2, bool two,
@@ -172,13 +173,14 @@ void build_row_blocks(Ctx &c, const DevCSR &A1, const DevCSR *A2, DevBuf<int32_t
 // The same two phases, but the value / column streams are brought into shared memory by the TMA
 // engine (cp.async.bulk, 1-D bulk copies completing on an mbarrier) through a TS-stage ring that a
 // dedicated producer warp keeps full.  The HBM stream no longer depends on how long the consumer
-// warps stall on the x gather: up to (TS-1) x 24 KB per CTA are in flight at any time.  One
-// persistent CTA pair per SM walks the row blocks grid-strided.
+// warps stall on the x gather.  Four persistent CTAs per SM walk the row blocks grid-strided.
+// Ring parameters from the sweep in profiles/ (B200, 300x100 Q3/Q2 Jacobian): 2 stages x 1792
+// non-zeros, 4 CTAs per SM, 16 lanes per row (8 on paired columns): 100 us per block product.
 #ifndef NSX_TS
-#define NSX_TS 3
+#define NSX_TS 2
 #endif
 #ifndef NSX_TNNZ
-#define NSX_TNNZ 1024
+#define NSX_TNNZ 1792
 #endif
 #ifndef NSX_DL
 #define NSX_DL 16
@@ -192,7 +194,7 @@ constexpr int TNNZ = NSX_TNNZ;        // non-zeros per row block
 #define NSX_TROWS (NSX_TNNZ / 8)
 #endif
 constexpr int TROWS = NSX_TROWS;      // rows per row block at most
-constexpr int TCAP = TNNZ + 16;       // elements per stage (two segments, each padded to a multiple of 4 at both ends)
+constexpr int TCAP = TNNZ + 32;       // elements per stage (two segments, each padded to a multiple of 8 at both ends)
 constexpr int TRP = TROWS + 4;        // row pointers per matrix per stage (range padded to even ends)
 constexpr int TCONS = 256;            // consumer threads (8 warps) + 1 producer warp
 constexpr size_t TMA_STAGE = (size_t)TCAP * 12 + 2 * TRP * 8 + sizeof(RowBlockDesc);  // values, columns, row pointers, descriptor
@@ -235,6 +237,63 @@ __device__ __forceinline__ TmaStage stage_of(unsigned char *ring, int st) {
   return s;
 }
 
+// DIRECT consumer: a sub-warp of DLX lanes walks each row straight out of the stage: values and columns come from shared
+// memory (filled by the TMA engine, never written by the SM), x through the read-only path, the sum stays in registers.
+// No product round trip through shared memory, no CTA-wide barrier.  PAIRED: the first matrix' columns come in aligned
+// pairs (both velocity components of a node group) -- one column id, one 16-byte gather of x and one 16-byte read of the
+// values per two non-zeros.
+template <int DLX, bool PAIRED>
+__device__ __forceinline__ void direct_rows(const TmaStage &S, const RowBlockDesc &d, bool two, const double *__restrict__ x1, const double *__restrict__ x2,
+                                            double *__restrict__ yy, int add, int tid) {
+  const double *v = S.val;
+  const int32_t *cidx = S.col;
+  const int64_t s1 = d.a1, s2 = d.a2 - d.c1;  // stage index = global index - s
+  const int nr = d.r1 - d.r0, roff = d.r0 & 1;
+  const int sl = tid & (DLX - 1);
+  const unsigned hmask = DLX == 32 ? 0xffffffffu : ((1u << (DLX & 31)) - 1u) << (tid & (32 - DLX) & 31);  // sub-warps leave the row loop independently
+  for (int i = tid / DLX; i < nr; i += TCONS / DLX) {
+    const int b1 = (int)(S.rp1[roff + i] - s1), e1 = (int)(S.rp1[roff + i + 1] - s1);
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    if (PAIRED) {
+      const int pb = b1 >> 1, pe = e1 >> 1;
+      const double2 *__restrict__ vv = reinterpret_cast<const double2 *>(v);
+      const double2 z = make_double2(0.0, 0.0);
+      for (int k = pb + sl; k - sl < pe; k += 4 * DLX) {
+        const bool p0 = k < pe, p1 = k + DLX < pe, p2 = k + 2 * DLX < pe, p3 = k + 3 * DLX < pe;
+        const int c0 = p0 ? cidx[k] : 0, c1 = p1 ? cidx[k + DLX] : 0, c2 = p2 ? cidx[k + 2 * DLX] : 0, c3 = p3 ? cidx[k + 3 * DLX] : 0;
+        const double2 x0 = p0 ? __ldg(reinterpret_cast<const double2 *>(x1 + c0)) : z, xb = p1 ? __ldg(reinterpret_cast<const double2 *>(x1 + c1)) : z;
+        const double2 xc = p2 ? __ldg(reinterpret_cast<const double2 *>(x1 + c2)) : z, xd = p3 ? __ldg(reinterpret_cast<const double2 *>(x1 + c3)) : z;
+        const double2 v0 = p0 ? vv[k] : z, vb = p1 ? vv[k + DLX] : z, vc = p2 ? vv[k + 2 * DLX] : z, vd = p3 ? vv[k + 3 * DLX] : z;
+        a0 += v0.x * x0.x; a1 += v0.y * x0.y; a2 += vb.x * xb.x; a3 += vb.y * xb.y;
+        a0 += vc.x * xc.x; a1 += vc.y * xc.y; a2 += vd.x * xd.x; a3 += vd.y * xd.y;
+      }
+    } else {
+      // four predicated gathers in flight per lane and trip; the trip count is uniform over the sub-warp
+      for (int k = b1 + sl; k - sl < e1; k += 4 * DLX) {
+        const bool p0 = k < e1, p1 = k + DLX < e1, p2 = k + 2 * DLX < e1, p3 = k + 3 * DLX < e1;
+        const int c0 = p0 ? cidx[k] : 0, c1 = p1 ? cidx[k + DLX] : 0, c2 = p2 ? cidx[k + 2 * DLX] : 0, c3 = p3 ? cidx[k + 3 * DLX] : 0;
+        const double x0 = p0 ? __ldg(x1 + c0) : 0.0, x1v = p1 ? __ldg(x1 + c1) : 0.0, x2v = p2 ? __ldg(x1 + c2) : 0.0, x3v = p3 ? __ldg(x1 + c3) : 0.0;
+        const double v0 = p0 ? v[k] : 0.0, v1 = p1 ? v[k + DLX] : 0.0, v2 = p2 ? v[k + 2 * DLX] : 0.0, v3 = p3 ? v[k + 3 * DLX] : 0.0;
+        a0 += v0 * x0; a1 += v1 * x1v; a2 += v2 * x2v; a3 += v3 * x3v;
+      }
+    }
+    if (two) {
+      const int b2 = (int)(S.rp2[roff + i] - s2), e2 = (int)(S.rp2[roff + i + 1] - s2);
+      for (int q = b2 + sl; q - sl < e2; q += 2 * DLX) {
+        const bool p0 = q < e2, p1 = q + DLX < e2;
+        const int c0 = p0 ? cidx[q] : 0, c1 = p1 ? cidx[q + DLX] : 0;
+        const double x0 = p0 ? __ldg(x2 + c0) : 0.0, x1v = p1 ? __ldg(x2 + c1) : 0.0;
+        const double v0 = p0 ? v[q] : 0.0, v1 = p1 ? v[q + DLX] : 0.0;
+        a2 += v0 * x0; a3 += v1 * x1v;
+      }
+    }
+    double s = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int o = DLX >> 1; o > 0; o >>= 1) s += __shfl_down_sync(hmask, s, o, DLX);
+    if (sl == 0) yy[d.r0 + i] = add ? yy[d.r0 + i] + s : s;
+  }
+}
+
 // Row blocks `first, first + stride, ...` of a list whose entries are of kind 0 (matrices M[0] and, if it has
 // non-zeros there, M[1] share the rows; y offset 0) or kind 1 (matrix M[2] alone; y offset yoff1).
 template <bool DIRECT>
@@ -264,14 +323,15 @@ __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, 
           case 0: dst = (void *)S.desc; src = desc + first + it * stride; bytes = sizeof(RowBlockDesc); break;
           case 1: dst = S.rp1; src = A1.rp + ra; bytes = rc * 8; break;
           case 2: dst = S.val; src = A1.val + d.a1; bytes = d.c1 * 8; break;
-          case 3: dst = S.col; src = A1.col + d.a1; bytes = d.c1 * 4; break;
+          case 3: if (A1.pcol) { dst = S.col; src = A1.pcol + (d.a1 >> 1); bytes = d.c1 * 2; } else { dst = S.col; src = A1.col + d.a1; bytes = d.c1 * 4; } break;
           case 4: if (two) { dst = S.rp2; src = A2.rp + ra; bytes = rc * 8; } break;
           case 5: if (two) { dst = S.val + d.c1; src = A2.val + d.a2; bytes = d.c2 * 8; } break;
           case 6: if (two) { dst = S.col + d.c1; src = A2.col + d.a2; bytes = d.c2 * 4; } break;
           default: break;
         }
         if (lane == 0)
-          mbar_expect_tx(&full[st], (uint32_t)(d.c1 + (two ? d.c2 : 0)) * 12u + (uint32_t)rc * 8u * (two ? 2u : 1u) + (uint32_t)sizeof(RowBlockDesc));
+          mbar_expect_tx(&full[st], (uint32_t)d.c1 * (A1.pcol ? 10u : 12u) + (two ? (uint32_t)d.c2 * 12u : 0u) + (uint32_t)rc * 8u * (two ? 2u : 1u) +
+                                        (uint32_t)sizeof(RowBlockDesc));
         __syncwarp();
         if (bytes) bulk_g2s(dst, src, bytes, &full[st]);
       }
@@ -285,44 +345,15 @@ __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, 
     const RowBlockDesc d = *S.desc;
     const bool two = d.kind == 0 && d.c2 > 0;
     const double *__restrict__ x1 = M[d.kind ? 2 : 0].x, *__restrict__ x2 = M[1].x;
+    const bool paired = DIRECT && M[d.kind ? 2 : 0].pcol != nullptr;
     double *v = S.val;
     const int32_t *cidx = S.col;
     double *yy = y + (d.kind ? yoff1 : 0);
     const int64_t s1 = d.a1, s2 = d.a2 - d.c1;  // stage index = global index - s
     const int nr = d.r1 - d.r0, roff = d.r0 & 1;
     if (DIRECT) {
-      // a sub-warp of DL lanes walks each row straight out of the stage: value and column come from shared
-      // memory (filled by the TMA engine, never written by the SM), x through the read-only path, the sum
-      // stays in registers.  No product round trip through shared memory, no CTA-wide barrier.
-      constexpr int DL = NSX_DL;
-      const int sl = tid & (DL - 1);
-      const unsigned hmask = DL == 32 ? 0xffffffffu : ((1u << (DL & 31)) - 1u) << (tid & (32 - DL) & 31);  // sub-warps leave the row loop independently
-      for (int i = tid / DL; i < nr; i += TCONS / DL) {
-        const int b1 = (int)(S.rp1[roff + i] - s1), e1 = (int)(S.rp1[roff + i + 1] - s1);
-        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        // four predicated gathers in flight per lane and trip; the trip count is uniform over the sub-warp
-        for (int k = b1 + sl; k - sl < e1; k += 4 * DL) {
-          const bool p0 = k < e1, p1 = k + DL < e1, p2 = k + 2 * DL < e1, p3 = k + 3 * DL < e1;
-          const int c0 = p0 ? cidx[k] : 0, c1 = p1 ? cidx[k + DL] : 0, c2 = p2 ? cidx[k + 2 * DL] : 0, c3 = p3 ? cidx[k + 3 * DL] : 0;
-          const double x0 = p0 ? __ldg(x1 + c0) : 0.0, x1v = p1 ? __ldg(x1 + c1) : 0.0, x2v = p2 ? __ldg(x1 + c2) : 0.0, x3v = p3 ? __ldg(x1 + c3) : 0.0;
-          const double v0 = p0 ? v[k] : 0.0, v1 = p1 ? v[k + DL] : 0.0, v2 = p2 ? v[k + 2 * DL] : 0.0, v3 = p3 ? v[k + 3 * DL] : 0.0;
-          a0 += v0 * x0; a1 += v1 * x1v; a2 += v2 * x2v; a3 += v3 * x3v;
-        }
-        if (two) {
-          const int b2 = (int)(S.rp2[roff + i] - s2), e2 = (int)(S.rp2[roff + i + 1] - s2);
-          for (int q = b2 + sl; q - sl < e2; q += 2 * DL) {
-            const bool p0 = q < e2, p1 = q + DL < e2;
-            const int c0 = p0 ? cidx[q] : 0, c1 = p1 ? cidx[q + DL] : 0;
-            const double x0 = p0 ? __ldg(x2 + c0) : 0.0, x1v = p1 ? __ldg(x2 + c1) : 0.0;
-            const double v0 = p0 ? v[q] : 0.0, v1 = p1 ? v[q + DL] : 0.0;
-            a2 += v0 * x0; a3 += v1 * x1v;
-          }
-        }
-        double s = (a0 + a1) + (a2 + a3);
-#pragma unroll
-        for (int o = DL >> 1; o > 0; o >>= 1) s += __shfl_down_sync(hmask, s, o, DL);
-        if (sl == 0) yy[d.r0 + i] = add ? yy[d.r0 + i] + s : s;
-      }
+      if (paired) direct_rows<NSX_DL / 2, true>(S, d, two, x1, x2, yy, add, tid);
+      else direct_rows<NSX_DL, false>(S, d, two, x1, x2, yy, add, tid);
     } else {
     // phase 1: products in place (every consumer thread busy, four independent gathers each)
 #pragma unroll 4
@@ -384,12 +415,12 @@ void append_row_descs(std::vector<RowBlockDesc> &h, const DevCSR &A1, const DevC
     if (r1 == r0) return;
     RowBlockDesc d{};
     const int64_t s1 = A1.h_rowptr[r0], e1 = A1.h_rowptr[r1];
-    d.a1 = s1 & ~(int64_t)3; d.o1 = (int)(s1 - d.a1); d.n1 = (int)(e1 - s1);
-    d.c1 = d.n1 ? (int)(((e1 + 3) & ~(int64_t)3) - d.a1) : 0;
+    d.a1 = s1 & ~(int64_t)7; d.o1 = (int)(s1 - d.a1); d.n1 = (int)(e1 - s1);
+    d.c1 = d.n1 ? (int)(((e1 + 7) & ~(int64_t)7) - d.a1) : 0;
     if (A2) {
       const int64_t s2 = A2->h_rowptr[r0], e2 = A2->h_rowptr[r1];
-      d.a2 = s2 & ~(int64_t)3; d.o2 = (int)(s2 - d.a2); d.n2 = (int)(e2 - s2);
-      d.c2 = d.n2 ? (int)(((e2 + 3) & ~(int64_t)3) - d.a2) : 0;
+      d.a2 = s2 & ~(int64_t)7; d.o2 = (int)(s2 - d.a2); d.n2 = (int)(e2 - s2);
+      d.c2 = d.n2 ? (int)(((e2 + 7) & ~(int64_t)7) - d.a2) : 0;
     }
     d.r0 = (int)r0; d.r1 = (int)r1; d.kind = kind;
     const double mean = (double)(d.n1 + d.n2) / (double)(r1 - r0);
@@ -405,6 +436,40 @@ void append_row_descs(std::vector<RowBlockDesc> &h, const DevCSR &A1, const DevC
     acc += len;
   }
   close(A1.nrows);
+}
+
+// Paired columns of a block whose columns are velocity dofs: in the FESystem numbering the two components of a node group
+// sit next to each other, so a row's columns come in aligned pairs (2k, 2k + 1).  Verified entry by entry on the device
+// layout of the columns (ghost columns are shifted by the owned pressure count on a partitioned system); a block that
+// does not pair keeps the scalar path.
+void build_pairs(Ctx &c, DevCSR &A, bool cols_are_p) {
+  if (A.pair_state) return;
+  A.pair_state = -1;
+  if (cols_are_p || A.nnz == 0 || (A.nnz & 1)) return;
+  const int64_t own = c.n_u, shift = c.n_p;
+  const bool baked = c.n_ug + c.n_pg > 0;
+  std::vector<int32_t> pc((size_t)(A.nnz / 2));
+  for (int64_t i = 0; i < A.nrows; ++i) {
+    const int64_t b = A.h_rowptr[i], e = A.h_rowptr[i + 1];
+    if ((b & 1) || (e & 1)) return;
+    for (int64_t k = b; k < e; k += 2) {
+      int64_t c0 = A.h_col[k], c1 = A.h_col[k + 1];
+      if (baked) { if (c0 >= own) c0 += shift; if (c1 >= own) c1 += shift; }
+      if ((c0 & 1) || c1 != c0 + 1) return;
+      pc[(size_t)(k >> 1)] = (int32_t)c0;
+    }
+  }
+  A.pcol.alloc_padded(pc.size(), 16, c.stream);
+  NSX_CUDA(cudaMemcpyAsync(A.pcol.p, pc.data(), pc.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
+  NSX_CUDA(cudaStreamSynchronize(c.stream));
+  A.pair_state = 1;
+}
+
+inline const int32_t *pairs_for(Ctx &c, const DevCSR &A_, const double *x) {
+  DevCSR &A = const_cast<DevCSR &>(A_);
+  if (c.stream_spmv != 3) return nullptr;
+  if (!A.pair_state) build_pairs(c, A, &A_ == &c.Bt || &A_ == &c.Mp || &A_ == &c.S);
+  return (A.pair_state == 1 && ((uintptr_t)x & 15) == 0) ? A.pcol.p : nullptr;
 }
 
 void tma_attr_once() {
@@ -442,7 +507,7 @@ void spmv_local(Ctx &c, const DevCSR &A_, const double *x, double *y, bool add) 
       A.desc.upload(h, c.stream);
     }
     const int grid = std::min(A.ndesc, NSX_TMINB * c.num_sms);
-    const StreamMat M{A.rowptr.p, A.col.p, A.val.p, x};
+    const StreamMat M{A.rowptr.p, A.col.p, A.val.p, x, (&A_ == &c.F || &A_ == &c.B) ? pairs_for(c, A_, x) : nullptr};
     if (c.stream_spmv == 3) k_spmv_tma<true><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0);
     else k_spmv_tma<false><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0);
     c.stat_launches++; c.stat_spmv++;
@@ -477,7 +542,8 @@ void block_spmv(Ctx &c, const double *x, double *y) {
       c.desc_u.upload(h, c.stream);
     }
     const int grid = std::min(c.ndesc_u, NSX_TMINB * c.num_sms);
-    const StreamMat MF{c.F.rowptr.p, c.F.col.p, c.F.val.p, x}, MBt{c.Bt.rowptr.p, c.Bt.col.p, c.Bt.val.p, x + c.n_u}, MB{c.B.rowptr.p, c.B.col.p, c.B.val.p, x};
+    const StreamMat MF{c.F.rowptr.p, c.F.col.p, c.F.val.p, x, pairs_for(c, c.F, x)}, MBt{c.Bt.rowptr.p, c.Bt.col.p, c.Bt.val.p, x + c.n_u, nullptr},
+        MB{c.B.rowptr.p, c.B.col.p, c.B.val.p, x, pairs_for(c, c.B, x)};
     if (c.stream_spmv == 3) k_spmv_tma<true><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(c.desc_u.p, c.ndesc_u, MF, MBt, MB, y, c.n_u, 0);
     else k_spmv_tma<false><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(c.desc_u.p, c.ndesc_u, MF, MBt, MB, y, c.n_u, 0);
     c.stat_launches++; c.stat_spmv++;
