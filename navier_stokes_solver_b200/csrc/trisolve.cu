@@ -275,15 +275,23 @@ template <bool SGS, bool FWD, int FTHREADS>
 __device__ __forceinline__ void finish_row_f(const TriArgs &A, const RowPreF &P, const double *sv, const int32_t *sc, const cg::thread_block_tile<FT> &tile) {
   if (P.row < 0) return;  // uniform over the tile
   const double *src = FWD ? A.w : A.yp;
-  double s0 = 0, s1 = 0;
-  int t = 0;
-  for (; t + 1 < P.cnt; t += 2) {
-    s0 += sv[t * FTHREADS] * __ldcg(src + sc[t * FTHREADS]);
-    s1 += sv[(t + 1) * FTHREADS] * __ldcg(src + sc[(t + 1) * FTHREADS]);
+  // eight predicated gathers of the work vector in flight per trip: a row of up to 8 x FT staged entries costs one L2
+  // round trip on the critical path instead of one per pair of entries
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (int t0 = 0; t0 < P.cnt; t0 += 8) {
+    double xv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) xv[u] = (t0 + u < P.cnt) ? __ldcg(src + sc[(t0 + u) * FTHREADS]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; u += 4) {
+      s0 += (t0 + u < P.cnt ? sv[(t0 + u) * FTHREADS] : 0.0) * xv[u];
+      s1 += (t0 + u + 1 < P.cnt ? sv[(t0 + u + 1) * FTHREADS] : 0.0) * xv[u + 1];
+      s2 += (t0 + u + 2 < P.cnt ? sv[(t0 + u + 2) * FTHREADS] : 0.0) * xv[u + 2];
+      s3 += (t0 + u + 3 < P.cnt ? sv[(t0 + u + 3) * FTHREADS] : 0.0) * xv[u + 3];
+    }
   }
-  if (t < P.cnt) s0 += sv[t * FTHREADS] * __ldcg(src + sc[t * FTHREADS]);
   for (int64_t k = P.rest_b; k < P.rest_e; k += FT) s1 += __ldcs(A.val + k) * __ldcg(src + __ldcs(A.col + k));
-  double s = s0 + s1;
+  double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
   for (int o = FT / 2; o > 0; o >>= 1) s += tile.shfl_down(s, o);
   if (tile.thread_rank() == 0) {

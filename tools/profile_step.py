@@ -22,7 +22,7 @@ ap.add_argument("--full", type=int, default=0)
 ap.add_argument("--kernels-only", action="store_true")
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--kernels", default="5,6,7,0,1,2,3,4")
-ap.add_argument("--spmv", type=int, default=2)
+ap.add_argument("--spmv", type=int, default=3)
 args = ap.parse_args()
 nx, ny = map(int, args.mesh.split(","))
 
