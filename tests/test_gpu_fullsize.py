@@ -1,0 +1,79 @@
+"""The README configuration at full size (-m 300,100: 29 738 cells, 657 740 DoFs, 41.2 M non-zeros) through
+size-independent properties -- the oracle would need minutes here, these identities need neither side:
+symmetry of the Stokes Jacobian before the Dirichlet step, B = Bt^T, Mp row sums = fluid area / nu, constant
+pressure in the kernel of Bt's interior rows, the block SpMV (TMA-fed kernel with paired columns) against a
+scipy product of the downloaded blocks, linearity of the product, SGS by its defining residual identity, and
+the row counts of SURVEY.md section 8."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import nsxlib as N
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big():
+    d = N.Disc.generate(300, 100)
+    dev = N.Device(d)
+    return d, dev
+
+
+def test_sizes_of_config_1(big):
+    d, dev = big
+    assert (d.ncells, d.n_u, d.n_p) == (29738, 537912, 119828)
+    assert [dev.nnz(b) for b in (N.BLOCK_F, N.BLOCK_BT, N.BLOCK_B, N.BLOCK_MP)] == [26790480, 7206232, 7206232, 1906736]
+
+
+def test_stokes_structure_at_full_size(big):
+    d, dev = big
+    nu = 0.1
+    dev.vec_set(N.VEC_SOLUTION, 0.0)
+    dev.assemble_cells(N.MODE_STOKES, nu)
+    F, Bt, B, Mp = (dev.csr(b) for b in (N.BLOCK_F, N.BLOCK_BT, N.BLOCK_B, N.BLOCK_MP))
+    assert abs(F - F.T).max() <= 1e-13 * abs(F).max()
+    assert abs(B - Bt.T).max() <= 1e-13 * abs(B).max()
+    cv = d.array("CELL_VERTICES").reshape(d.ncells, d.nvpc, 2)
+    area = np.sum((cv[:, 1, 0] - cv[:, 0, 0]) * (cv[:, 2, 1] - cv[:, 0, 1]))
+    assert abs(Mp.sum() * nu - area) <= 1e-11 * area
+    flux = Bt @ np.ones(d.n_p)
+    interior = np.ones(d.n_u, bool)
+    interior[d.array("BC_DOF")] = False
+    out = d.array("CELL_DOFS").reshape(d.ncells, -1)[d.array("OUTLET_CELL")].ravel()
+    interior[out[out < d.n_u]] = False
+    assert np.abs(flux[interior]).max() <= 1e-12
+
+
+def test_block_spmv_and_sgs_at_full_size(big):
+    d, dev = big
+    dev.upload(N.VEC_SOLUTION, N.synthetic_state(d, 1234))
+    dev.assemble(N.MODE_NEWTON, False, 1 / 90.0)
+    F, Bt, B = (dev.csr(b) for b in (N.BLOCK_F, N.BLOCK_BT, N.BLOCK_B))
+    J = sp.bmat([[F, Bt], [B, None]], format="csr")
+    rng = np.random.default_rng(42)
+    x, z = rng.uniform(-1, 1, d.n), rng.uniform(-1, 1, d.n)
+    ref = J @ x
+    for flag in (3, 2, 1, 0):           # every SpMV kernel: same product up to summation order
+        dev.set_option(N.OPT_STREAM_SPMV, flag)
+        y = dev.spmv(N.BLOCK_J, x)
+        assert np.abs(y - ref).max() <= 1e-13 * np.abs(ref).max(), flag
+        yf = dev.spmv(N.BLOCK_F, x[: d.n_u])
+        assert np.abs(yf - F @ x[: d.n_u]).max() <= 1e-13 * np.abs(ref).max(), flag
+    dev.set_option(N.OPT_STREAM_SPMV, 3)
+    # linearity: J (a x + z) = a J x + J z
+    lin = dev.spmv(N.BLOCK_J, 0.37 * x + z)
+    assert np.abs(lin - (0.37 * ref + J @ z)).max() <= 1e-12 * np.abs(ref).max()
+    # multicolour SGS by definition: y = (D + U)^-1 D (D + L)^-1 x in the elimination order  <=>
+    # (D + L) D^-1 (D + U) y = x on the permuted matrix
+    xu = x[: d.n_u]
+    y = dev.inner_apply(N.BLOCK_F, 0, xu)
+    perm = dev.ordering(N.BLOCK_F)
+    Fp = F[perm][:, perm].tocsr()
+    Dg = Fp.diagonal()
+    Lo, Up = sp.tril(Fp, -1, format="csr"), sp.triu(Fp, 1, format="csr")
+    yp = y[perm]
+    t = Dg * yp + Up @ yp                      # (D + U) y
+    lhs = t + Lo @ (t / Dg)                    # (D + L) D^-1 t
+    assert np.abs(lhs - xu[perm]).max() <= 1e-11 * np.abs(xu).max()
+    assert dev.stat("LEVELS_F") <= 64
