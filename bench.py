@@ -348,7 +348,7 @@ def main():
         kernels[k]["ms_l2_flushed_single_launch"] = k_flushed[k]
         kernels[k]["ms_back_to_back"] = k_b2b[k]
     dom = max(share, key=share.get)
-    dom_kernel = {"sgs_F": "k_sweep_coop<SGS> (symmetric Gauss-Seidel sweeps on F, inner preconditioner)",
+    dom_kernel = {"sgs_F": "k_sweep_phased<SGS> (symmetric Gauss-Seidel sweeps on F, inner preconditioner of the inner FGMRES)",
                   "spmv_F": "k_spmv_tma (F SpMV of the inner FGMRES)", "block_spmv": "k_spmv_tma (Jacobian block SpMV)"}[dom]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
