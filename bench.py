@@ -154,17 +154,116 @@ def run_reference(args, emit):
     emit(line)
 
 
+def run_unsteady(args, emit):
+    """--workload unsteady: seconds per time step of NSSolver on the reference's gmsh mesh (tests/golden/new_mesh.msh.gz,
+    P2/P1, 117 273 DoFs), Re = 100, dt = 0.01, FGMRES + aSIMPLE (BASELINE config 3).  A step is what NSSolver::solve does per time
+    step (lab_new/src/NSSolver.cpp:814-835): solution_old = solution, solve_newton with its Reynolds continuation 1, 11, ..., 91
+    (each stage: assemble / solve / line search until the residual stalls), lift and drag.  One GPU."""
+    import ctypes
+    import gzip
+    import shutil
+    import tempfile
+    import torch
+    from navier_stokes_solver_b200 import binding as B
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("the unsteady workload runs on one GPU (aSIMPLE on a partitioned system is not built yet)")
+    mesh = os.path.join(tempfile.gettempdir(), "nsx_bench_new_mesh.msh")
+    if not os.path.exists(mesh):
+        with gzip.open(os.path.join(ROOT, "tests", "golden", "new_mesh.msh.gz"), "rb") as f, open(mesh, "wb") as g:
+            shutil.copyfileobj(f, g)
+    d = B.Disc.from_gmsh(mesh)
+    stream = torch.cuda.Stream()
+    dev = B.Device(d, inlet_amplitude=0.3, stream=ctypes.c_void_p(stream.cuda_stream))
+    Re, dt, tol = 100.0, 0.01, args.tol if args.tol != 1e-10 else 1e-6   # the CLI default tolerance of the unsteady binary
+    state = {"apply_first": True}
+    log = {}
+
+    def time_step():
+        dev.copy_old()
+        first_iter = True
+        outer, solves, assemblies = 0, 0, 0
+        nu = 1.0
+        cur = 1.0
+        while cur <= Re:
+            nu = 1.0 / cur
+            n_iter, res, prev = 0, 1e-9 + 1, 0.0
+            while n_iter < 10 and res > 1e-9:
+                if first_iter:
+                    first_iter = False
+                    fi = n_iter == 0
+                else:
+                    fi = False
+                res = dev.assemble(B.MODE_UNSTEADY_FIRST if fi else B.MODE_UNSTEADY_NEWTON, fi and state["apply_first"], nu, dt)
+                assemblies += 1
+                prev = res + 1 if n_iter == 0 else prev
+                if res <= 1e-9:
+                    break
+                rc, it, fr = dev.solve(B.UNSTEADY, 1, 2, tol, 100000)
+                if rc != 0:
+                    raise SystemExit(f"solve failed rc={rc}: {dev.last_error()}")
+                outer += it
+                solves += 1
+                if it == 0:
+                    break
+                dev.save_eval_point()
+                alpha = 1.0
+                while alpha > 1e-12:
+                    dev.update(alpha)
+                    res = dev.assemble(B.MODE_UNSTEADY_NEWTON, False, nu, dt)
+                    assemblies += 1
+                    if res <= prev:
+                        break
+                    alpha *= 0.1
+                prev = res
+                n_iter += 1
+            cur += 10.0
+        state["apply_first"] = False
+        drag, lift = dev.lift_drag(nu)
+        log.update(outer=outer, solves=solves, assemblies=assemblies, drag=drag, lift=lift)
+
+    for _ in range(args.warmup):
+        time_step()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev.synchronize(); torch.cuda.synchronize()
+    l0 = dev.stat("KERNEL_LAUNCHES")
+    e0.record(stream)
+    for _ in range(args.steps):
+        time_step()
+    e1.record(stream)
+    dev.synchronize(); torch.cuda.synchronize()
+    val = e0.elapsed_time(e1) / 1e3 / args.steps
+    launches = dev.stat("KERNEL_LAUNCHES") - l0
+    clocks = sampler.stop()
+    U_avg = 2 * 0.3 / 3
+    emit({"metric": "s per time step", "value": val, "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": val * 1e3,
+          "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "reference mesh (lab_new/mesh/new_mesh.msh), zero initial state",
+          "config": {"workload": f"NSSolver -M -r 100 -T 8,0.01 -s 1 -t {tol:g} -p 2: time steps {args.warmup + 1}..{args.warmup + args.steps} (10 Reynolds stages per step)",
+                     "cells": d.ncells, "dofs": d.n, "outer_iterations_last_step": log["outer"], "solves_last_step": log["solves"],
+                     "assemblies_last_step": log["assemblies"], "drag_coefficient": 2 * log["drag"] / (U_avg ** 2 * 0.1), "lift_coefficient": 2 * log["lift"] / (U_avg ** 2 * 0.1),
+                     "l2_policy": "whole-step timing; the 117 k-DoF matrices (43 MB) fit L2, as they do in the reference configuration"},
+          "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16 * (log["assemblies"] + 2 * log["solves"]) + 16},
+          "gpu_launches": launches, "clocks": clocks})
+    dev.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="nsx", choices=["nsx", "reference"])
+    ap.add_argument("--workload", default="stationary", choices=["stationary", "unsteady"],
+                    help="stationary: README configuration (default, the headline); unsteady: BASELINE config 3, seconds per time step")
     ap.add_argument("--mesh", default="300,100")
     ap.add_argument("--solver", type=int, default=1)
     ap.add_argument("--prec", type=int, default=0)
     ap.add_argument("--tol", type=float, default=1e-10)
     ap.add_argument("--ordering", type=int, default=1, help="ILU/SGS elimination order: 0 natural (as Ifpack), 1 multicolour")
+    ap.add_argument("--ortho", type=int, default=None, help="Gram-Schmidt variant (NSX_OPT_ORTHO); default: the library's")
     ap.add_argument("--cpu-outer-cap", type=int, default=1)
     ap.add_argument("--cpu-outer-total", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
@@ -180,6 +279,8 @@ def main():
 
     if args.impl == "reference":
         return run_reference(args, emit)
+    if args.workload == "unsteady":
+        return run_unsteady(args, emit)
 
     import ctypes
     import torch
@@ -208,10 +309,10 @@ def main():
         d = g.local(rank)
         ids = [B.Device.new_comm_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
-        dev = B.Device(d, device_id=local_rank, ordering=args.ordering, comm_id=ids[0], stream=ctypes.c_void_p(stream.cuda_stream))
+        dev = B.Device(d, device_id=local_rank, ordering=args.ordering, ortho=args.ortho, comm_id=ids[0], stream=ctypes.c_void_p(stream.cuda_stream))
     else:
         d = g
-        dev = B.Device(d, device_id=local_rank, ordering=args.ordering, stream=ctypes.c_void_p(stream.cuda_stream))
+        dev = B.Device(d, device_id=local_rank, ordering=args.ordering, ortho=args.ortho, stream=ctypes.c_void_p(stream.cuda_stream))
     setup_s = time.perf_counter() - t0
 
     n = dev.n   # owned entries of this rank
@@ -356,7 +457,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload_name(args, nx, ny), "cells": g.ncells, "dofs": g.n, "nnz_J_rank0": nnz_j,
                    "partition": f"{world} strips of cells, owned rows per rank (rank 0: {n} dofs)" if world > 1 else "one rank",
-                   "elimination_order": "multicolour" if args.ordering else "natural",
+                   "elimination_order": "multicolour" if args.ordering else "natural", "ortho_option": args.ortho,
                    "outer_iterations": stats["outer"], "inner_F_iterations": stats["inner_F"], "inner_Mp_or_S_iterations": stats["inner_S"],
                    "final_residual": stats["final_res"],
                    "l2_policy": "step: working set (0.5 GB matrix + 60 Krylov vectors) exceeds the 126 MB L2; kernel timings: SpMV / sweep inputs (330-510 MB) exceed L2 and are timed back to back in one event pair (the L2-flushed single-launch times are listed beside them), vector kernels flush L2 (512 MiB) before every launch",

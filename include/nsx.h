@@ -38,7 +38,8 @@ enum nsx_flavour { NSX_STATIONARY = 0, NSX_UNSTEADY = 1 }; /* which header's pre
 enum nsx_option {
   NSX_OPT_ORDERING = 0,   /* elimination order of ILU(0)/SGS: 0 natural (as Ifpack), 1 multicolour (default) */
   NSX_OPT_VERBOSE = 1,
-  NSX_OPT_ORTHO = 2,      /* Gram-Schmidt of GMRES/FGMRES: 0 modified chain (as deal.II), 1 batched classical, two passes (default) */
+  NSX_OPT_ORTHO = 2,      /* Gram-Schmidt of GMRES/FGMRES: 0 modified chain (as deal.II), 1 batched classical, two passes (default),
+                             2 as 1 for the outer solver, one pass + conditional second pass for the inner FGMRES solves */
   NSX_OPT_COOP_SWEEP = 3, /* ILU/SGS sweeps: 1 colour-phased persistent kernel with its own grid barrier (default, multicolour order), 2 level-phased cooperative launch, 0 one launch per level */
   NSX_OPT_STREAM_SPMV = 4 /* SpMV kernel: 3 TMA-fed persistent, rows reduced from the stage, paired velocity columns (default); 2 TMA-fed, products staged; 1 streaming with plain loads; 0 sub-warp per row */
 };

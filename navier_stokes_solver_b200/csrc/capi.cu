@@ -122,7 +122,9 @@ int nsx_set_option(nsx_ctx *ctx, int option, int64_t value) {
         if (value != 0 && value != 1) throw std::invalid_argument("ordering must be 0 (natural) or 1 (multicolour)");
         ctx->ordering = (int)value; break;
       case NSX_OPT_VERBOSE: ctx->verbose = (int)value; break;
-      case NSX_OPT_ORTHO: ctx->ortho = value ? 1 : 0; break;
+      case NSX_OPT_ORTHO:
+        if (value < 0 || value > 2) throw std::invalid_argument("orthogonalisation must be 0, 1 or 2");
+        ctx->ortho = (int)value; break;
       case NSX_OPT_COOP_SWEEP:
         if (value < 0 || value > 2) throw std::invalid_argument("sweep kernel must be 0 (a launch per level), 1 (colour-phased persistent) or 2 (level-phased cooperative)");
         ctx->coop_sweep = (int)value; break;

@@ -153,6 +153,27 @@ void solver_fgmres(Ctx &c, Control &ctl, const DOp &A, double *x, const double *
         read_slots(c, slot0, j + 2, hs);
         for (int i = 0; i <= j; ++i) H[j][i] = hs[i];
         H[j][j + 1] = a = std::sqrt(hs[j + 1]);
+      } else if (c.ortho == 2 && slot0 != 0) {
+        // inner solves (tolerances 1e-1 ... 1e-5 relative): one pass of batched classical Gram-Schmidt, and a second one
+        // only when the first removed more than 99 % of the vector's square norm (|w'|^2 < 0.01 (|w'|^2 + sum h^2)), i.e.
+        // when cancellation would cost more than a digit of orthogonality.  deal.II's SolverFGMRES itself orthogonalises
+        // once (modified Gram-Schmidt, no second pass).
+        VecList V;
+        for (int i = 0; i <= j; ++i) V.v[i] = v(i);
+        vec_multi_dot_dev(c, slot0, V, j + 1, aux, n);
+        vec_multi_axpy_norm_dev(c, slot0 + 64, V, j + 1, slot0, aux, n);
+        read_slots(c, slot0, 65, hs);
+        double h2 = 0;
+        for (int i = 0; i <= j; ++i) { H[j][i] = hs[i]; h2 += hs[i] * hs[i]; }
+        double nrm2 = hs[64];
+        if (nrm2 < 0.01 * (nrm2 + h2)) {
+          vec_multi_dot_dev(c, slot0 + 32, V, j + 1, aux, n);
+          vec_multi_axpy_norm_dev(c, slot0 + 65, V, j + 1, slot0 + 32, aux, n);
+          read_slots(c, slot0 + 32, 34, hs + 32);
+          for (int i = 0; i <= j; ++i) H[j][i] += hs[32 + i];
+          nrm2 = hs[65];
+        }
+        H[j][j + 1] = a = std::sqrt(nrm2);
       } else {  // two passes of batched classical Gram-Schmidt: 4 launches and one host read per column
         VecList V;
         for (int i = 0; i <= j; ++i) V.v[i] = v(i);
