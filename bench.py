@@ -169,15 +169,23 @@ def run_unsteady(args, emit):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     if int(os.environ.get("WORLD_SIZE", "1")) != 1:
         raise SystemExit("the unsteady workload runs on one GPU (aSIMPLE on a partitioned system is not built yet)")
-    mesh = os.path.join(tempfile.gettempdir(), "nsx_bench_new_mesh.msh")
-    if not os.path.exists(mesh):
-        with gzip.open(os.path.join(ROOT, "tests", "golden", "new_mesh.msh.gz"), "rb") as f, open(mesh, "wb") as g:
-            shutil.copyfileobj(f, g)
-    d = B.Disc.from_gmsh(mesh)
+    if args.unsteady_mesh == "gmsh":
+        mesh = os.path.join(tempfile.gettempdir(), "nsx_bench_new_mesh.msh")
+        if not os.path.exists(mesh):
+            with gzip.open(os.path.join(ROOT, "tests", "golden", "new_mesh.msh.gz"), "rb") as f, open(mesh, "wb") as g:
+                shutil.copyfileobj(f, g)
+        d = B.Disc.from_gmsh(mesh)
+        mesh_flag = "-M"
+    elif args.unsteady_mesh.startswith("tri:"):
+        d = B.Disc.generate(*parse_mesh(args.unsteady_mesh[4:]), triangles=True)   # P2/P1 on the generated channel (every quad split in two)
+        mesh_flag = f"-M [generated {args.unsteady_mesh[4:]} grid split into triangles]"
+    else:
+        d = B.Disc.generate(*parse_mesh(args.unsteady_mesh))
+        mesh_flag = f"-m {args.unsteady_mesh}"
     stream = torch.cuda.Stream()
-    dev = B.Device(d, inlet_amplitude=0.3, stream=ctypes.c_void_p(stream.cuda_stream))
+    dev = B.Device(d, inlet_amplitude=0.3, ordering=args.ordering, ortho=args.ortho, stream=ctypes.c_void_p(stream.cuda_stream))
     Re, dt, tol = 100.0, 0.01, args.tol if args.tol != 1e-10 else 1e-6   # the CLI default tolerance of the unsteady binary
-    state = {"apply_first": True}
+    state = {"apply_first": True, "n": 0}
     log = {}
 
     def time_step():
@@ -202,7 +210,8 @@ def run_unsteady(args, emit):
                     break
                 rc, it, fr = dev.solve(B.UNSTEADY, 1, 2, tol, 100000)
                 if rc != 0:
-                    raise SystemExit(f"solve failed rc={rc}: {dev.last_error()}")
+                    raise SystemExit(f"solve failed rc={rc} in time step {state['n'] + 1}, Re stage {cur:g}, Newton iteration {n_iter}, after {solves} solves "
+                                     f"({outer} outer iterations) of this step: {dev.last_error()}")
                 outer += it
                 solves += 1
                 if it == 0:
@@ -220,6 +229,7 @@ def run_unsteady(args, emit):
                 n_iter += 1
             cur += 10.0
         state["apply_first"] = False
+        state["n"] += 1
         drag, lift = dev.lift_drag(nu)
         log.update(outer=outer, solves=solves, assemblies=assemblies, drag=drag, lift=lift)
 
@@ -240,8 +250,8 @@ def run_unsteady(args, emit):
     clocks = sampler.stop()
     U_avg = 2 * 0.3 / 3
     emit({"metric": "s per time step", "value": val, "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": val * 1e3,
-          "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "reference mesh (lab_new/mesh/new_mesh.msh), zero initial state",
-          "config": {"workload": f"NSSolver -M -r 100 -T 8,0.01 -s 1 -t {tol:g} -p 2: time steps {args.warmup + 1}..{args.warmup + args.steps} (10 Reynolds stages per step)",
+          "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "reference mesh (lab_new/mesh/new_mesh.msh) or generated channel mesh, zero initial state",
+          "config": {"workload": f"NSSolver {mesh_flag} -r 100 -T 8,0.01 -s 1 -t {tol:g} -p 2: time steps {args.warmup + 1}..{args.warmup + args.steps} (10 Reynolds stages per step)",
                      "cells": d.ncells, "dofs": d.n, "outer_iterations_last_step": log["outer"], "solves_last_step": log["solves"],
                      "assemblies_last_step": log["assemblies"], "drag_coefficient": 2 * log["drag"] / (U_avg ** 2 * 0.1), "lift_coefficient": 2 * log["lift"] / (U_avg ** 2 * 0.1),
                      "l2_policy": "whole-step timing; the 117 k-DoF matrices (43 MB) fit L2, as they do in the reference configuration"},
@@ -263,6 +273,7 @@ def main():
     ap.add_argument("--prec", type=int, default=0)
     ap.add_argument("--tol", type=float, default=1e-10)
     ap.add_argument("--ordering", type=int, default=1, help="ILU/SGS elimination order: 0 natural (as Ifpack), 1 multicolour")
+    ap.add_argument("--unsteady-mesh", default="gmsh", help="unsteady workload: 'gmsh' = the reference's new_mesh.msh (P2/P1), X,Y = generated Q3/Q2 mesh, tri:X,Y = generated P2/P1 mesh")
     ap.add_argument("--ortho", type=int, default=None, help="Gram-Schmidt variant (NSX_OPT_ORTHO); default: the library's")
     ap.add_argument("--cpu-outer-cap", type=int, default=1)
     ap.add_argument("--cpu-outer-total", type=int, default=0)

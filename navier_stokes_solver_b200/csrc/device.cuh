@@ -137,7 +137,7 @@ struct Ctx {
   std::string err;
   int verbose = 0;
   int ordering = 1;
-  int ortho = 1;        // 0 modified Gram-Schmidt chain (as deal.II), 1 batched classical Gram-Schmidt with re-orthogonalisation
+  int ortho = 2;        // 0 modified Gram-Schmidt chain (as deal.II), 1 batched classical Gram-Schmidt twice, 2 (default) as 1 for the outer solver and a conditional second pass for the inner FGMRES solves
   int stream_spmv = 3;  // 3: TMA-fed persistent SpMV, rows reduced straight from the stage, paired columns (default); 2: same ring, products staged in shared memory; 1: streaming with plain loads; 0: sub-warp per row
   DevBuf<RowBlockDesc> desc_u, desc_p;
   int ndesc_u = 0, ndesc_p = 0;
