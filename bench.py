@@ -111,9 +111,9 @@ def cpu_step_sample(disc, solver, prec, tol, nu, outer_cap, threads=None):
     return t_asm, t_solve, max(it, 1), int(orc().orc_get_threads())
 
 
-# outer FGMRES iterations of the full solve, measured on the B200 (bench_r1.json): the CPU sample runs a few outer
+# outer FGMRES iterations of the full solve, measured on the B200 (profiles/r01_bench_1gpu_300x100.json): the CPU sample runs a few outer
 # iterations and is scaled linearly to this count (early iterations are the cheap ones, so the scaling favours the CPU)
-MEASURED_OUTER = {("300,100", 1, 0): 814}
+MEASURED_OUTER = {("300,100", 1, 0): 817}
 
 
 def workload_name(args, nx, ny):
@@ -459,6 +459,9 @@ def main():
         kernels[k]["est_share_of_step"] = v
         kernels[k]["ms_l2_flushed_single_launch"] = k_flushed[k]
         kernels[k]["ms_back_to_back"] = k_b2b[k]
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture of
+    # this configuration on one B200 (profiles/r01_prof_r1_top_kernels.md); null for any other mesh / partition
+    ncu_traffic = {"sgs_F": 478.5e6 + 11.9e6, "block_spmv": 448.1e6 + 9.2e6, "spmv_F": 278.4e6 + 7.9e6} if (args.mesh == "300,100" and world == 1) else {}
     dom = max(share, key=share.get)
     dom_kernel = {"sgs_F": "k_sweep_phased<SGS> (symmetric Gauss-Seidel sweeps on F, inner preconditioner of the inner FGMRES)",
                   "spmv_F": "k_spmv_tma (F SpMV of the inner FGMRES)", "block_spmv": "k_spmv_tma (Jacobian block SpMV)"}[dom]
@@ -478,10 +481,10 @@ def main():
         "spmv_launches_rank0": spmv_calls,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                     "frac": kernels[dom]["GBps"] / peak, "traffic": None, "peak_kind": peak_kind,
+                     "frac": kernels[dom]["GBps"] / peak, "traffic": ncu_traffic.get(dom), "peak_kind": peak_kind,
                      "algorithmic_bytes": kernels[dom].get("algorithmic_bytes", spmv_f_bytes), "est_share_of_step": share[dom]},
         "spmv_roofline": {"kernel": "k_spmv_tma (Jacobian block SpMV)", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
-                          "algorithmic_bytes": bts},
+                          "algorithmic_bytes": bts, "traffic": ncu_traffic.get("block_spmv")},
         "kernels": kernels,
     }
     if rank == 0 and not args.no_cpu and world == 1:
