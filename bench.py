@@ -424,6 +424,11 @@ def main():
     k_flushed = dict(k_ms)
     if g.n > 300000:   # only when the matrices really exceed L2
         k_ms.update(k_b2b)
+    # FP64 FMA peak of this GPU, measured in the same run (the denominator of the assembly's FP64 utilisation)
+    dev.time_kernel(20, 2, False)
+    fp64_ms = dev.time_kernel(20, 5, False)
+    n_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    fp64_peak_tflops = n_sms * 8 * 256 * 8192 * 8 * 2 / (fp64_ms * 1e-3) / 1e12
     clocks = sampler.stop() if rank == 0 else None
 
     nnz = {b: dev.nnz(b) for b in (B.BLOCK_F, B.BLOCK_BT, B.BLOCK_B, B.BLOCK_MP)}
@@ -443,6 +448,8 @@ def main():
         "spmv_F": {"ms": k_ms["spmv_F"], "GBps": spmv_f_bytes / (k_ms["spmv_F"] * 1e-3) / 1e9,
                    "frac_hbm": spmv_f_bytes / (k_ms["spmv_F"] * 1e-3) / 1e9 / peak},
         "assembly_newton": {"ms": k_ms["assembly_newton"], "GFLOPs_fp64": 1.206e5 * ncells_own / (k_ms["assembly_newton"] * 1e-3) / 1e9,
+                            "fp64_peak_measured_TFLOPs": fp64_peak_tflops,
+                            "fp64_utilisation": 1.206e5 * ncells_own / (k_ms["assembly_newton"] * 1e-3) / 1e12 / fp64_peak_tflops,
                             "GBps_min_bytes": asm_bytes / (k_ms["assembly_newton"] * 1e-3) / 1e9},
         "dot": {"ms": k_ms["dot"], "GBps": 16 * n / (k_ms["dot"] * 1e-3) / 1e9},
         "axpy": {"ms": k_ms["axpy"], "GBps": 24 * n / (k_ms["axpy"] * 1e-3) / 1e9},

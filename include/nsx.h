@@ -146,7 +146,8 @@ int nsx_schur(nsx_ctx *ctx);
 int nsx_precond_apply(nsx_ctx *ctx, int flavour, int prec, double alpha, int vec_src, int vec_dst);
 /* times `reps` launches of one kernel with CUDA events on the context's stream; ms per launch.
  * what: 0 Jacobian block SpMV, 1 F SpMV, 2 assembly (matrix + rhs kernels), 3 dot, 4 axpy, 5 SGS(F) apply,
- * 6 ILU(F) apply, 7 ILU(F) factorisation.  nsx_set_time_params picks the assembly branch that `what` = 2 times. */
+ * 6 ILU(F) apply, 7 ILU(F) factorisation, 20 an FP64 FMA peak kernel (num_SMs x 8 x 256 threads x 8192 x 8 FMAs).
+ * nsx_set_time_params picks the assembly branch that `what` = 2 times. */
 int nsx_set_time_params(nsx_ctx *ctx, int mode, double nu, double dt);
 /* flush_l2: 1 = L2 flushed before every launch, one event pair per launch; 0 = no flush; 2 = `reps` launches back to back inside one
  * event pair (for kernels whose input is larger than L2: no launch / event overhead in the figure). */

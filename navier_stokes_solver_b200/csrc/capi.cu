@@ -541,6 +541,7 @@ int nsx_time_kernel(nsx_ctx *ctx, int what, int reps, int flush_l2, double *ms_p
         case 7: ilu0_factor(c, *P, c.F); break;
         case 8: spmv_probe(c, c.F, 0, x, y); break;   // stream F's values + columns only
         case 9: spmv_probe(c, c.F, 1, x, y); break;   // ... plus the x gather
+        case 20: fp64_peak_launch(c, y); break;        // FP64 FMA peak: 148 x 8 x 256 threads x 8192 x 8 FMAs = 39.7 GFlop per launch
         default: throw std::invalid_argument("unknown kernel id");
       }
       if (back_to_back) continue;

@@ -238,6 +238,8 @@ double read_slot(Ctx &c, int slot);
 void read_slots(Ctx &c, int first, int count, double *out);
 double vec_dot(Ctx &c, const double *a, const double *b, int64_t n);
 void flush_l2_cache(Ctx &c, int round);
+constexpr int FP64_PEAK_ITERS = 8192;
+double fp64_peak_launch(Ctx &c, double *sink);   // launches the FP64 FMA peak kernel; returns the flops of the launch
 double vec_norm(Ctx &c, const double *a, int64_t n);
 double vec_add_and_dot(Ctx &c, double *w, double a, const double *x, const double *v, int64_t n);
 

@@ -289,6 +289,25 @@ void flush_l2_cache(Ctx &c, int round) {
   k_flush_read<<<c.num_sms * 8, 256, 0, c.stream>>>((const int4 *)(c.flush.p + half), (int64_t)(half / sizeof(int4)), (int *)c.flush.p);
 }
 
+// FP64 FMA peak of the device (measurement only): 8 independent dependent chains per thread, FP64_PEAK_ITERS trips
+__global__ void __launch_bounds__(256) k_fp64_peak(double *sink, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double m = 1.0000001, b = 1e-9;
+#pragma unroll 8
+  for (int i = 0; i < FP64_PEAK_ITERS; ++i) {
+    a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+    a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+  }
+  const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 1.2345e-300) *sink = s;
+}
+double fp64_peak_launch(Ctx &c, double *sink) {
+  const int grid = c.num_sms * 8;
+  k_fp64_peak<<<grid, 256, 0, c.stream>>>(sink, 0.5);
+  c.stat_launches++;
+  return (double)grid * 256.0 * FP64_PEAK_ITERS * 8.0 * 2.0;  // flops of one launch
+}
+
 double vec_dot(Ctx &c, const double *a, const double *b, int64_t n) {
   vec_dot_dev(c, RED_SLOTS - 1, a, b, n);
   return read_slot(c, RED_SLOTS - 1);
