@@ -31,11 +31,21 @@ def run():
     assert rc_o == 0 and rc_d == 0, (rc_o, rc_d)
     x_o, x_d = orc.vec(2), dev.download(B.VEC_DELTA)
     assert np.linalg.norm(x_d - x_o) <= 1e-7 * np.linalg.norm(x_o)
+    # the same system once more in the library's default configuration (multicolour elimination order: colour-phased persistent
+    # sweep kernel; batched Gram-Schmidt): another preconditioner, the same solution
+    dev.set_option(B.OPT_ORDERING, 1)
+    dev.upload(B.VEC_DELTA, np.zeros(d.n))
+    dev.assemble(B.MODE_NEWTON, True, nu)
+    rc_m, it_m, _ = dev.solve(B.STATIONARY, 1, 2, 1e-10, 4000)
+    assert rc_m == 0, rc_m
+    x_m = dev.download(B.VEC_DELTA)
+    assert np.linalg.norm(x_m - x_o) <= 1e-7 * np.linalg.norm(x_o)
+    dev.set_option(B.OPT_ORDERING, 0)
     dev.save_eval_point()
     dev.update(1.0)
     orc.vec(0)[:] = sol + x_o
     dd, ld = dev.lift_drag(nu)
     do, lo = orc.lift_drag(nu)
     assert abs(dd - do) <= 1e-6 * abs(do) and abs(ld - lo) <= 1e-6 * max(abs(lo), abs(do))
-    print(f"smoke ok: {d.ncells} cells, {d.n} dofs, FGMRES+aSIMPLE iterations gpu {it_d} / oracle {it_o}, "
+    print(f"smoke ok: {d.ncells} cells, {d.n} dofs, FGMRES+aSIMPLE iterations gpu {it_d} / oracle {it_o} (multicolour order: {it_m}), "
           f"kernel launches {dev.stat('KERNEL_LAUNCHES')}")
