@@ -4,8 +4,15 @@
 // inside every Krylov solver of the reference (NSSolverStationary.cpp:589-637,
 // NSSolverStationary.hpp:140, 198, 207, 288, 292, 305; NSSolver.hpp:226, 324, 345).
 //
+// Kernels, in the order the dispatch prefers them (NSX_OPT_STREAM_SPMV):
+//   3 (default)  k_spmv_tma<true>: persistent CTAs, a producer warp keeps a shared-memory ring of row blocks full with
+//                1-D TMA bulk copies, consumer sub-warps reduce each row straight from the stage; columns of F and B
+//                (velocity dofs) come in aligned pairs: one column id and one 16-byte x gather per two non-zeros
+//   2            k_spmv_tma<false>: same ring, products parked in the stage, then reduced per row
+//   1            k_spmv_stream / k_block_spmv_stream: plain coalesced loads through shared memory
+//   0            k_spmv / k_block_spmv: a sub-warp per row (also used for the small AMG level operators)
 // Layout: one CSR per block (F n_u x n_u, Bt n_u x n_p, B n_p x n_u, Mp, S), 64-bit row
-// pointers, 32-bit block-local columns, FP64 values.  A sub-warp of G lanes owns a row, so the
+// pointers, 32-bit block-local columns, FP64 values.  In kernel 0 a sub-warp of G lanes owns a row, so the
 // lanes of a warp stream 32/G consecutive rows = one contiguous span of the value / column
 // arrays (coalesced, streamed with ld.global.cs so that x stays cached), x is gathered through
 // the read-only path, and the row sum is a log2(G) shuffle reduction (deterministic order).

@@ -6,10 +6,12 @@
 //   PreconditionBlockDiagonal / BlockTriangular / aSIMPLE in both flavours
 //   (NSSolverStationary.hpp:115-335, NSSolver.hpp:138-384).
 // The iteration logic (what deal.II's solvers do step by step, default AdditionalData) runs on the
-// host; every vector lives on the device and all arithmetic on vectors is a CUDA kernel.  The
-// modified Gram-Schmidt chains of GMRES / FGMRES pass their coefficients from kernel to kernel in
-// device memory (add_and_dot fused kernels), so one orthogonalisation costs one host read, not
-// one per basis vector.
+// host; every vector lives on the device and all arithmetic on vectors is a CUDA kernel.
+// Orthogonalisation of GMRES / FGMRES (NSX_OPT_ORTHO): 0 = deal.II's modified Gram-Schmidt as a chain of fused
+// add_and_dot kernels that hand their coefficients on in device memory; 1 = two passes of batched classical
+// Gram-Schmidt (all dot products of a pass in one launch, all updates + the norm in another); 2 (default) = as 1 for
+// the outer solver, and for the inner FGMRES solves one pass plus a second only after heavy cancellation.  Every
+// variant costs one host read per Krylov iteration, not one per basis vector.
 #include <cmath>
 #include <functional>
 #include <limits>

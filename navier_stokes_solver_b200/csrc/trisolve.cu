@@ -10,13 +10,15 @@
 // Both operators are a lower sweep followed by an upper sweep over the same sparse matrix:
 //   SGS : w = (D + L)^-1 x ,  y = w - D^-1 U y          (== Ifpack's two Gauss-Seidel passes)
 //   ILU : w = L^-1 x       ,  y = U^-1 w                 (L unit lower, U upper incl. diagonal)
-// The plan stores the block permuted by the elimination order (natural = Ifpack's, or a greedy
-// multicolouring that shortens the dependency chains from thousands of levels to ~100), its
-// rows grouped by dependency level.  A level with many rows is one grid launch (a sub-warp per
-// row, shuffle-free strided partial sums reduced inside the sub-warp); runs of consecutive small
-// levels are chained inside ONE thread block with __syncthreads() between levels, which removes
-// the launch latency that dominates the natural order.  The ILU(0) factorisation runs over the
-// same level schedule.
+// The plan stores the block permuted by the elimination order, its rows grouped by dependency level:
+//   * natural order (Ifpack's; NSX_OPT_ORDERING = 0, parity runs): thousands of short levels.  A level with many rows
+//     is one grid launch (a sub-warp per row); runs of consecutive small levels are chained inside ONE thread block
+//     with __syncthreads() between levels, which removes the launch latency that dominates this order;
+//   * multicolour order (default): a greedy colouring re-sorted by dependency level (32 levels for Q3/Q2, each a
+//     contiguous row range for both sweeps) and ONE persistent launch per application, k_sweep_phased below:
+//     colour phases separated by a hand-rolled grid barrier, the next phase's rows staged in shared memory with
+//     cp.async while the barrier is in flight.
+// The ILU(0) factorisation runs over the same level schedule (one launch per level).
 #include <cooperative_groups.h>
 
 #include <algorithm>
