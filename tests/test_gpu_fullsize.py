@@ -77,3 +77,41 @@ def test_block_spmv_and_sgs_at_full_size(big):
     lhs = t + Lo @ (t / Dg)                    # (D + L) D^-1 t
     assert np.abs(lhs - xu[perm]).max() <= 1e-11 * np.abs(xu).max()
     assert dev.stat("LEVELS_F") <= 64
+
+
+SLOW_PATH_SCRIPT = r'''
+import os, sys
+import numpy as np, scipy.sparse as sp
+sys.path.insert(0, os.path.join(os.environ["NSX_ROOT"], "tests")); sys.path.insert(0, os.environ["NSX_ROOT"])
+import nsxlib as N
+d = N.Disc.generate(300, 100)
+dev = N.Device(d)
+dev.upload(N.VEC_SOLUTION, N.synthetic_state(d, 1234))
+dev.assemble(N.MODE_NEWTON, False, 1 / 90.0)
+F = dev.csr(N.BLOCK_F)
+x = np.random.default_rng(7).uniform(-1, 1, d.n_u)
+y = dev.inner_apply(N.BLOCK_F, 0, x)
+perm = dev.ordering(N.BLOCK_F)
+yp, xp = y[perm], x[perm]
+# SGS: (D + L) D^-1 (D + U) y = x on the permuted matrix
+Fp = F[perm][:, perm].tocsr()
+Dg = Fp.diagonal()
+t = Dg * yp + sp.triu(Fp, 1, format="csr") @ yp
+lhs = t + sp.tril(Fp, -1, format="csr") @ (t / Dg)
+assert np.abs(lhs - xp).max() <= 1e-11 * np.abs(x).max()
+print("SLOW_PATH_OK levels", dev.stat("LEVELS_F"))
+'''
+
+
+def test_sweep_rows_beyond_the_grid(tmp_path):
+    """With 256 threads per CTA the persistent sweep covers 9 472 rows per phase, fewer than a level of the 300x100 block
+    holds (~16 800): the rows beyond the grid take the stage-and-consume path inside the same phase."""
+    import os
+    import subprocess
+    import sys
+    script = tmp_path / "slow_path.py"
+    script.write_text(SLOW_PATH_SCRIPT)
+    env = dict(os.environ, NSX_ROOT=N.ROOT, NSX_SWEEP_THREADS="256")
+    r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "SLOW_PATH_OK" in r.stdout
