@@ -66,6 +66,19 @@ def test_banner_and_short_M_swallows_the_next_flag(tmp_path):
     assert "    velocity = 104066\n    pressure = 13207\n    total    = 117273" in out
 
 
+def test_long_options(tmp_path):
+    """Long options as declared at testStationary.cpp:33-42 / test.cpp:37-47: --read-mesh-from-file takes NO argument (so the
+    mesh size that follows it is kept, unlike after the short -M), the others take one."""
+    r = run(UNST, "--read-mesh-from-file", "--mesh-size", "7,3", "--reynolds", "50", "--solver", "2", "--tolerance", "1e-8", "--preconditioner", "2",
+            "--timespan-step", "0.5,0.05", env={"NSX_MESH_FILE": N.golden_mesh_path()}, cwd=tmp_path)
+    assert "Time span: 0.5\nTime step: 0.05\nMesh size: 7x3\nReynolds number: 50\nSolver type: Bicgstab\nTolerance: 1e-08\nPreconditioner: aSIMPLE\n" in r.stdout
+    assert "Mesh file name = " in r.stdout and "  Velocity degree:           = 2" in r.stdout      # the file mesh / P2-P1 element was selected
+    r = run(STAT, "--solver", "9", "--preconditioner", "5", "--mesh-size", "4,2", cwd=tmp_path)    # values outside {0,1,2} print nothing after the label
+    assert "Solver type: Tolerance: 1e-06\nPreconditioner: -----------------------------------------------\n" in r.stdout
+    r = run(STAT, "--timespan-step", "1,0.1")                                                      # not an option of the stationary binary
+    assert r.returncode == 1 and "Usage:" in r.stdout
+
+
 def test_generated_mesh_setup_prints_the_reference_dof_count(tmp_path):
     """100x70 -> 154244 DoFs (performance_analysis.ipynb): the one integer the reference pins."""
     r = run(UNST, "-m", "100,70", "-T", "0.02,0.01", cwd=tmp_path)
