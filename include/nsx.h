@@ -36,12 +36,18 @@ enum nsx_vec { NSX_VEC_SOLUTION = 0, NSX_VEC_SOLUTION_OLD = 1, NSX_VEC_DELTA = 2
 enum nsx_mode { NSX_MODE_STOKES = 0, NSX_MODE_NEWTON = 1, NSX_MODE_UNSTEADY_FIRST = 2, NSX_MODE_UNSTEADY_NEWTON = 3 };
 enum nsx_flavour { NSX_STATIONARY = 0, NSX_UNSTEADY = 1 }; /* which header's preconditioner internals */
 enum nsx_option {
-  NSX_OPT_ORDERING = 0,   /* elimination order of ILU(0)/SGS: 0 natural (as Ifpack), 1 multicolour (default) */
+  NSX_OPT_ORDERING = 0,   /* elimination order of ILU(0)/SGS: 0 natural (as Ifpack), 1 multicolour over the whole owned range,
+                             2 (default) the owned range cut into spatially compact blocks (one CTA each, the structure of the
+                             reference's overlap-0 Ifpack preconditioners under mpirun -n <#blocks>), multicolour inside a block */
   NSX_OPT_VERBOSE = 1,
   NSX_OPT_ORTHO = 2,      /* Gram-Schmidt of GMRES/FGMRES: 0 modified chain (as deal.II), 1 batched classical, two passes (default),
                              2 as 1 for the outer solver, one pass + conditional second pass for the inner FGMRES solves */
   NSX_OPT_COOP_SWEEP = 3, /* ILU/SGS sweeps: 1 colour-phased persistent kernel with its own grid barrier (default, multicolour order), 2 level-phased cooperative launch, 0 one launch per level */
-  NSX_OPT_STREAM_SPMV = 4 /* SpMV kernel: 3 TMA-fed persistent, rows reduced from the stage, paired velocity columns (default); 2 TMA-fed, products staged; 1 streaming with plain loads; 0 sub-warp per row */
+  NSX_OPT_STREAM_SPMV = 4, /* SpMV kernel: 3 TMA-fed persistent, rows reduced from the stage, paired velocity columns (default); 2 TMA-fed, products staged; 1 streaming with plain loads; 0 sub-warp per row */
+  NSX_OPT_BLOCK_ROWS = 5, /* ordering 2: target rows per block (0 = automatic: rows / #SMs clamped to [512, 4096]) */
+  NSX_OPT_HOST_INNER = 6  /* 1: the inner FGMRES solves run their recurrences on the host (one stream synchronisation per
+                             iteration, round-1 behaviour); 0 (default): device-side Givens / convergence decision, the host
+                             polls a mapped record and launches the next sweep speculatively */
 };
 enum nsx_stat {
   NSX_STAT_INNER_F = 0, NSX_STAT_INNER_S = 1, NSX_STAT_PRECOND_APPLIES = 2, NSX_STAT_KERNEL_LAUNCHES = 3,
@@ -155,6 +161,9 @@ int nsx_time_kernel(nsx_ctx *ctx, int what, int reps, int flush_l2, double *ms_p
 int nsx_synchronize(nsx_ctx *ctx);
 /* elimination order used for a block's ILU/SGS (new -> old), for oracle parity */
 int nsx_get_ordering(nsx_ctx *ctx, int block, int32_t *perm);
+/* ordering 2: the blocks of the block-local sweeps -- block b eliminates perm[offsets[b] .. offsets[b+1]) in that order and
+ * drops its couplings to other blocks; n_blocks = 0 for orderings 0 / 1.  offsets (n_blocks + 1 entries) may be NULL. */
+int nsx_get_sweep_blocks(nsx_ctx *ctx, int block, int32_t *n_blocks, int64_t *offsets);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ MODE_STOKES, MODE_NEWTON, MODE_UNSTEADY_FIRST, MODE_UNSTEADY_NEWTON = 0, 1, 2, 3
 VEC_SOLUTION, VEC_SOLUTION_OLD, VEC_DELTA, VEC_RESIDUAL, VEC_EVAL, VEC_TMP0, VEC_TMP1 = 0, 1, 2, 3, 4, 5, 6
 STATIONARY, UNSTEADY = 0, 1
 NSX_OK, NSX_E_NOCONV, NSX_E_BADARG, NSX_E_CUDA, NSX_E_COMM, NSX_E_STATE = 0, 1, 2, 3, 4, 5
-OPT_ORDERING, OPT_VERBOSE, OPT_ORTHO, OPT_COOP_SWEEP, OPT_STREAM_SPMV = 0, 1, 2, 3, 4
+OPT_ORDERING, OPT_VERBOSE, OPT_ORTHO, OPT_COOP_SWEEP, OPT_STREAM_SPMV, OPT_BLOCK_ROWS, OPT_HOST_INNER = 0, 1, 2, 3, 4, 5, 6
 STAT = dict(INNER_F=0, INNER_S=1, PRECOND_APPLIES=2, KERNEL_LAUNCHES=3, LEVELS_F=4, LEVELS_MP=5, LEVELS_S=6,
             SPMV_CALLS=7, ASSEMBLY_COLOURS=8, ASSEMBLY_TABLES=9, LAST_STEP=10, HALO_EXCHANGES=11, ALLREDUCES=12)
 # every entry point include/nsx.h declares (tests check that the library exports each one)
@@ -40,7 +40,7 @@ NSX_SYMBOLS = ["nsx_create", "nsx_destroy", "nsx_last_error", "nsx_set_option", 
                "nsx_get_block_values", "nsx_set_block_values", "nsx_spmv", "nsx_inner_apply", "nsx_ilu0_factor",
                "nsx_schur", "nsx_precond_apply", "nsx_set_time_params", "nsx_time_kernel", "nsx_synchronize",
                "nsx_get_ordering", "nsx_set_partition", "nsx_set_halo", "nsx_comm_unique_id", "nsx_comm_init",
-               "nsx_halo_exchange", "nsx_vec_download_ghosts"]
+               "nsx_halo_exchange", "nsx_vec_download_ghosts", "nsx_get_sweep_blocks"]
 NSX_HOST_SYMBOLS = ["nsx_disc_generate", "nsx_disc_from_gmsh", "nsx_disc_local", "nsx_disc_free", "nsx_host_last_error", "nsx_disc_info",
                     "nsx_disc_array", "nsx_disc_inlet_values"]
 
@@ -105,6 +105,7 @@ def nsx():
         L.nsx_time_kernel.argtypes = [vp, i32, i32, i32, c_dp]
         L.nsx_synchronize.argtypes = [vp]
         L.nsx_get_ordering.argtypes = [vp, i32, vp]
+        L.nsx_get_sweep_blocks.argtypes = [vp, i32, C.POINTER(i32), vp]
         L.nsx_set_partition.argtypes = [vp, i64, i64]
         L.nsx_set_halo.argtypes = [vp, i32, i32, vp, vp, vp, vp]
         L.nsx_comm_unique_id.argtypes = [vp]
@@ -217,7 +218,7 @@ class Device:
     """One GPU context of the hot path (include/nsx.h) filled from a Disc.  Every method is a thin call
     through the C ABI; there is no CPU fallback (construction fails without a CUDA device)."""
 
-    def __init__(self, disc, device_id=0, inlet_amplitude=0.1, ordering=None, stream=None, ortho=None, comm_id=None):
+    def __init__(self, disc, device_id=0, inlet_amplitude=0.1, ordering=None, stream=None, ortho=None, comm_id=None, block_rows=None):
         """disc: a global Disc (one GPU) or a local view (Disc.local(rank)) of a partitioned run; for the
         latter comm_id is the 128-byte NCCL id shared by all ranks (Device.new_comm_id() on rank 0)."""
         L = nsx()
@@ -235,6 +236,8 @@ class Device:
             self._ck(L.nsx_set_option(self.h, OPT_ORDERING, ordering))
         if ortho is not None:
             self._ck(L.nsx_set_option(self.h, OPT_ORTHO, ortho))
+        if block_rows is not None:
+            self._ck(L.nsx_set_option(self.h, OPT_BLOCK_ROWS, block_rows))
         cd = np.ascontiguousarray(disc.array("CELL_DOFS"))
         cv = np.ascontiguousarray(disc.array("CELL_VERTICES"))
         self._ck(L.nsx_set_discretisation(self.h, disc.elem, disc.ncells, ptr(cv), ptr(cd), disc.n_u, disc.n_p))
@@ -410,6 +413,17 @@ class Device:
         perm = np.empty(nrows, dtype=np.int32)
         self._ck(nsx().nsx_get_ordering(self.h, block, ptr(perm)))
         return perm
+
+    def sweep_blocks(self, block):
+        """(offsets, perm) of the block-local sweeps (ordering 2): block b eliminates perm[offsets[b]:offsets[b+1]] in that order;
+        None for the other orderings."""
+        nb = C.c_int32()
+        self._ck(nsx().nsx_get_sweep_blocks(self.h, block, C.byref(nb), None))
+        if nb.value == 0:
+            return None
+        off = np.empty(nb.value + 1, dtype=np.int64)
+        self._ck(nsx().nsx_get_sweep_blocks(self.h, block, C.byref(nb), ptr(off)))
+        return off, self.ordering(block)
 
     def schur(self):
         self._ck(nsx().nsx_schur(self.h))

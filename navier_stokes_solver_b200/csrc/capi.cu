@@ -107,6 +107,7 @@ int nsx_destroy(nsx_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   comm_destroy(*ctx);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+  if (ctx->fg_rec) cudaFreeHost(ctx->fg_rec);
   cudaStream_t s = ctx->own_stream ? ctx->stream : nullptr;
   delete ctx;
   if (s) cudaStreamDestroy(s);
@@ -119,8 +120,11 @@ int nsx_set_option(nsx_ctx *ctx, int option, int64_t value) {
   return guarded(ctx, [&] {
     switch (option) {
       case NSX_OPT_ORDERING:
-        if (value != 0 && value != 1) throw std::invalid_argument("ordering must be 0 (natural) or 1 (multicolour)");
+        if (value < 0 || value > 2) throw std::invalid_argument("ordering must be 0 (natural), 1 (multicolour) or 2 (multicolour inside CTA-local blocks)");
         ctx->ordering = (int)value; break;
+      case NSX_OPT_BLOCK_ROWS:
+        if (value < 0 || value > 4096) throw std::invalid_argument("block rows must lie in [0, 4096] (0: automatic)");
+        ctx->block_rows = (int)value; ctx->tri.clear(); break;
       case NSX_OPT_VERBOSE: ctx->verbose = (int)value; break;
       case NSX_OPT_ORTHO:
         if (value < 0 || value > 2) throw std::invalid_argument("orthogonalisation must be 0, 1 or 2");
@@ -131,6 +135,7 @@ int nsx_set_option(nsx_ctx *ctx, int option, int64_t value) {
       case NSX_OPT_STREAM_SPMV:
         if (value < 0 || value > 3) throw std::invalid_argument("SpMV kernel must be 0, 1, 2 or 3");
         ctx->stream_spmv = (int)value; break;
+      case NSX_OPT_HOST_INNER: ctx->host_inner = value != 0; break;
       default: throw std::invalid_argument("unknown option");
     }
   });
@@ -504,6 +509,15 @@ int nsx_get_ordering(nsx_ctx *ctx, int block, int32_t *perm) {
   return guarded(ctx, [&] {
     TriPlan &P = tri_plan(*ctx, block);
     std::copy(P.h_perm.begin(), P.h_perm.end(), perm);
+  });
+}
+
+int nsx_get_sweep_blocks(nsx_ctx *ctx, int block, int32_t *n_blocks, int64_t *offsets) {
+  return guarded(ctx, [&] {
+    TriPlan &P = tri_plan(*ctx, block);
+    if (!n_blocks) throw std::invalid_argument("null output pointer");
+    *n_blocks = P.nblk;
+    if (offsets) std::copy(P.blk_off.begin(), P.blk_off.end(), offsets);
   });
 }
 

@@ -94,6 +94,8 @@ struct DevCSR {
 // dropped: the reference's Ifpack preconditioners run with overlap 0), permuted by the
 // elimination order (natural as Ifpack, or multicolour), rows grouped by dependency level.
 struct TriStep { int kind, l0, l1; };   // kind 0: one wide level as a grid launch; 1: levels [l0,l1) chained in one CTA
+// one block of the block-local sweep: its slice of the value / index streams, its passes, its rows
+struct alignas(16) BlkDesc { long long val_base, idx_base; int pass0, npass, row0, nrows; };
 struct TriPlan {
   int64_t n = 0, nnz = 0;
   int ordering = 0;
@@ -117,6 +119,19 @@ struct TriPlan {
   std::vector<int64_t> h_rowptr, lvl_f, lvl_b;
   std::vector<int32_t> h_col, h_diag, h_perm;
   std::vector<TriStep> steps_f, steps_b;
+  // block-local sweeps (ordering 2, sweep_block.cu): the rows are cut into spatially compact blocks, one CTA each; block b
+  // owns the permuted rows [blk_off[b], blk_off[b+1]), sorted by their dependency level inside the block (h_level)
+  int nblk = 0;
+  std::vector<int64_t> blk_off;
+  std::vector<int32_t> h_level;
+  DevBuf<double> bl_val;                // value sections of all passes (ELL slices + reciprocal diagonals)
+  DevBuf<uint16_t> bl_idx;              // index sections (block-local columns + row slots)
+  DevBuf<int64_t> bl_map;               // per entry of bl_val: (index into val << 2) | kind
+  DevBuf<int4> bl_pass;                 // pass headers
+  DevBuf<BlkDesc> bl_blk;               // block descriptors
+  int64_t bl_nval = 0;
+  int bl_max_rows = 0, bl_max_pass = 0, bl_stage_val = 0, bl_stage_idx = 0;   // sizes of the shared-memory areas (elements)
+  int bl_sgs = -1;                      // what the stream currently holds: 1 SGS values, 0 ILU factors, -1 nothing
 };
 
 struct AmgHierarchy;  // amg.cu
@@ -136,7 +151,13 @@ struct Ctx {
   bool own_stream = false;
   std::string err;
   int verbose = 0;
-  int ordering = 1;
+  int ordering = 2;      // ILU / SGS elimination order: 0 natural (Ifpack), 1 multicolour over the owned range, 2 (default) multicolour inside CTA-local blocks
+  int block_rows = 0;    // ordering 2: target rows per block (0: n / #SMs clamped to [512, 4096])
+  bool host_inner = false;  // inner FGMRES recurrences on the host (round-1 behaviour) instead of the device
+  // device-driven inner FGMRES (krylov.cu): recurrence state in device memory, its verdicts mirrored in a mapped host record
+  DevBuf<unsigned char> fg_dev;
+  void *fg_rec = nullptr;        // pinned, mapped
+  long long fg_seq = 0;
   int ortho = 2;        // 0 modified Gram-Schmidt chain (as deal.II), 1 batched classical Gram-Schmidt twice, 2 (default) as 1 for the outer solver and a conditional second pass for the inner FGMRES solves
   int stream_spmv = 3;  // 3: TMA-fed persistent SpMV, rows reduced straight from the stage, paired columns (default); 2: same ring, products staged in shared memory; 1: streaming with plain loads; 0: sub-warp per row
   DevBuf<RowBlockDesc> desc_u, desc_p;
@@ -233,6 +254,29 @@ double *slot_ptr(Ctx &c, int slot);
 // batched classical Gram-Schmidt pass: slot0+m <- v_m . w (m < k) ; then w -= sum_m slot[m] v_m, slot_norm <- w . w
 void vec_multi_dot_dev(Ctx &c, int slot0, const VecList &V, int k, const double *w, int64_t n);
 void vec_multi_axpy_norm_dev(Ctx &c, int slot_norm, const VecList &V, int k, int slot_coef, double *w, int64_t n);
+// ---- device-driven inner FGMRES (SolverFGMRES on one block; deal.II's recurrences restated on the device) ----
+// Recurrence state of one solve in device memory.  Instead of deal.II's Householder least-squares solve of the whole
+// Hessenberg matrix in every iteration, the columns are reduced by Givens rotations as they arrive: the residual of the
+// (j+1) x j problem deal.II checks at step j is |g[j]|, and the same y comes out of the back substitution.
+struct FgDev {
+  double R[30][32];     // rotated Hessenberg columns (upper triangular)
+  double g[32], cs[32], sn[32], y[32], hsave[32];
+  double a, tol, res;   // a: norm of the vector the next basis vector is scaled from
+  int it, max_it, ny, gate;   // gate: 0 go on, 1 second Gram-Schmidt pass wanted, 2 converged, 3 failed
+};
+struct FgRec { long long seq; int gate, it, ny, pad; double res; };   // mirror of the verdicts in mapped host memory
+FgDev *fg_state(Ctx &c);   // allocates the state + record on first use
+// res = sqrt(*beta2); verdict of SolverControl::check(it0, res); starts a restart cycle
+void fg_begin(Ctx &c, const double *beta2, double tol, int max_it, int it0);
+// column j of the cycle: mode 0 = coefficients slots[0..j] + square norm slots[j+1] (modified Gram-Schmidt chain);
+// 1 = first classical pass (slots[0..j], slots[64]), asks for a second pass after heavy cancellation; 2 = that second
+// pass (adds slots[32..], norm slots[65]); 3 = two passes done up front
+void fg_step(Ctx &c, const double *slots, int j, int mode);
+FgRec fg_wait(Ctx &c);     // spins on the mapped record until the last fg_begin / fg_step has landed
+// v = x / *a (zero if *a is not finite), skipped when *gate != 0
+void vec_scale_to_dev(Ctx &c, double *v, const double *x, const double *a, const int *gate, int64_t n);
+// x += sum_{m < *count} coef[m] V_m  (count and coefficients read on the device)
+void vec_multi_add_dev(Ctx &c, double *x, const VecList &V, const double *coef, const int *count, int64_t n);
 // blocking reads of device scalars
 double read_slot(Ctx &c, int slot);
 void read_slots(Ctx &c, int first, int count, double *out);
@@ -264,6 +308,16 @@ void ilu0_factor(Ctx &c, TriPlan &P, const DevCSR &A);
 void ilu0_apply(Ctx &c, TriPlan &P, double *y, const double *x);
 void sgs_apply(Ctx &c, TriPlan &P, double *y, const double *x);
 DevCSR &block_ref(Ctx &c, int block);
+
+// ---- sweep_block.cu -------------------------------------------------------------------------
+// cuts the rows [lo, hi) of a square block into spatially compact groups (weighted recursive coordinate bisection of the
+// dof positions implied by the cell table); grp[i] = first_group + k
+int geometric_blocks(Ctx &c, int block, const DevCSR &A, int64_t lo, int64_t hi, int first_group, std::vector<int32_t> &grp);
+void bl_build(Ctx &c, TriPlan &P);                       // streams + descriptors of the block-local sweep
+void bl_refresh(Ctx &c, TriPlan &P, bool sgs);           // stream values from P.val (after tri_refresh_values / ilu0_factor)
+// y = M^-1 x.  Fused variants for the inner FGMRES: x is scaled by 1 / *scale on the way in and the scaled vector is
+// also stored to v_out; the launch does nothing when *gate != 0 (speculative launch behind a device-side decision).
+void bl_sweep(Ctx &c, TriPlan &P, bool sgs, double *y, const double *x, const double *scale = nullptr, double *v_out = nullptr, const int *gate = nullptr);
 
 // ---- spgemm.cu ------------------------------------------------------------------------------
 void schur_symbolic(Ctx &c);

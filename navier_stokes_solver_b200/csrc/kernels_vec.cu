@@ -6,6 +6,8 @@
 // Reductions are two-stage and deterministic: fixed grid, per-CTA partials in a fixed order, the
 // last CTA to finish sums them.  Results stay in device "slots" so that dependent kernels
 // (the modified Gram-Schmidt chain) read their coefficient without a host round trip.
+#include <cstring>
+
 #include "device.cuh"
 
 namespace nsx {
@@ -185,9 +187,141 @@ __global__ void __launch_bounds__(VT) k_multi_axpy_norm(VecList V, int k, const 
   }
 }
 
+__global__ void __launch_bounds__(VT) k_scale_to(double *__restrict__ v, const double *__restrict__ x, const double *a, const int *gate, int64_t n) {
+  if (gate && *gate != 0) return;
+  const double av = *a;
+  const bool ok = isfinite(av);
+  const double inv = 1.0 / av;
+  for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT) v[i] = ok ? inv * x[i] : 0.0;
+}
+
+__global__ void __launch_bounds__(VT) k_multi_add(double *__restrict__ x, VecList V, const double *coef, const int *count, int64_t n) {
+  __shared__ const double *sv[32];
+  __shared__ double sc[32];
+  const int k = *count;
+  if (threadIdx.x < 32) { sv[threadIdx.x] = V.v[threadIdx.x]; sc[threadIdx.x] = threadIdx.x < k ? coef[threadIdx.x] : 0.0; }
+  __syncthreads();
+  if (k <= 0) return;
+  for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT) {
+    double xi = x[i];
+    for (int m = 0; m < k; ++m) xi += sc[m] * sv[m][i];
+    x[i] = xi;
+  }
+}
+
+__device__ __forceinline__ int fg_check(const FgDev *st, int step, double value) {  // SolverControl::check -> gate code
+  if (value <= st->tol) return 2;
+  if (step >= st->max_it || isnan(value)) return 3;
+  return 0;
+}
+__device__ __forceinline__ void fg_publish(const FgDev *st, FgRec *rec, long long seq) {
+  rec->gate = st->gate; rec->it = st->it; rec->ny = st->ny; rec->res = st->res;
+  __threadfence_system();
+  *(volatile long long *)&rec->seq = seq;
+}
+
+__global__ void k_fg_begin(FgDev *st, const double *beta2, double tol, int max_it, int it0, FgRec *rec, long long seq) {
+  const double beta = sqrt(*beta2);
+  st->tol = tol; st->max_it = max_it; st->it = it0; st->ny = 0;
+  st->res = beta; st->a = beta; st->g[0] = beta;
+  const int v = fg_check(st, it0, beta);
+  st->gate = v == 2 ? 2 : 0;   // deal.II leaves the cycle at its start only on success
+  fg_publish(st, rec, seq);
+}
+
+__global__ void k_fg_step(FgDev *st, const double *slots, int j, int mode, FgRec *rec, long long seq) {
+  if (st->gate >= 2) { fg_publish(st, rec, seq); return; }
+  double *col = st->R[j];
+  double nrm2;
+  if (mode == 0) {
+    for (int i = 0; i <= j; ++i) col[i] = slots[i];
+    nrm2 = slots[j + 1];
+  } else if (mode == 1) {
+    double h2 = 0;
+    for (int i = 0; i <= j; ++i) { col[i] = slots[i]; h2 += slots[i] * slots[i]; }
+    nrm2 = slots[64];
+    if (nrm2 < 0.01 * (nrm2 + h2)) { st->gate = 1; fg_publish(st, rec, seq); return; }
+  } else {
+    for (int i = 0; i <= j; ++i) col[i] = (mode == 2 ? col[i] : slots[i]) + slots[32 + i];
+    nrm2 = slots[65];
+  }
+  st->gate = 0;
+  const double a = sqrt(nrm2);
+  st->a = a;
+  int verdict = 0;
+  if (j > 0) {
+    st->res = fabs(st->g[j]);
+    verdict = fg_check(st, ++st->it, st->res);
+  }
+  if (verdict != 0 || j == 29) {   // y of the (j+1) x j least-squares problem: back substitution in the rotated columns
+    for (int i = j - 1; i >= 0; --i) {
+      double s = st->g[i];
+      for (int cc = i + 1; cc < j; ++cc) s -= st->R[cc][i] * st->y[cc];
+      st->y[i] = s / st->R[i][i];
+    }
+    st->ny = j;
+    st->gate = verdict;
+    if (verdict == 0 && j == 29) st->gate = 0;
+    fg_publish(st, rec, seq);
+    return;
+  }
+  col[j + 1] = a;
+  for (int i = 0; i < j; ++i) {
+    const double t = st->cs[i] * col[i] + st->sn[i] * col[i + 1];
+    col[i + 1] = -st->sn[i] * col[i] + st->cs[i] * col[i + 1];
+    col[i] = t;
+  }
+  const double r = 1.0 / sqrt(col[j] * col[j] + col[j + 1] * col[j + 1]);
+  st->sn[j] = col[j + 1] * r;
+  st->cs[j] = col[j] * r;
+  col[j] = st->cs[j] * col[j] + st->sn[j] * col[j + 1];
+  st->g[j + 1] = -st->sn[j] * st->g[j];
+  st->g[j] *= st->cs[j];
+  fg_publish(st, rec, seq);
+}
+
 }  // namespace
 
 #define LAUNCHED(c) ((c).stat_launches++)
+
+FgDev *fg_state(Ctx &c) {
+  if (!c.fg_dev.p) {
+    c.fg_dev.alloc(sizeof(FgDev));
+    c.fg_dev.zero(c.stream);
+    NSX_CUDA(cudaHostAlloc(&c.fg_rec, sizeof(FgRec), cudaHostAllocMapped));
+    memset(c.fg_rec, 0, sizeof(FgRec));
+    c.fg_seq = 0;
+  }
+  return reinterpret_cast<FgDev *>(c.fg_dev.p);
+}
+void fg_begin(Ctx &c, const double *beta2, double tol, int max_it, int it0) {
+  FgDev *st = fg_state(c);
+  k_fg_begin<<<1, 1, 0, c.stream>>>(st, beta2, tol, max_it, it0, (FgRec *)c.fg_rec, ++c.fg_seq); LAUNCHED(c);
+}
+void fg_step(Ctx &c, const double *slots, int j, int mode) {
+  FgDev *st = fg_state(c);
+  k_fg_step<<<1, 1, 0, c.stream>>>(st, slots, j, mode, (FgRec *)c.fg_rec, ++c.fg_seq); LAUNCHED(c);
+}
+FgRec fg_wait(Ctx &c) {
+  const FgRec *rec = (const FgRec *)c.fg_rec;
+  for (unsigned long long spins = 0;; ++spins) {
+    if (__atomic_load_n(&rec->seq, __ATOMIC_ACQUIRE) == c.fg_seq) break;
+    if ((spins & 0xfffff) == 0xfffff) {   // every ~1M polls: has the stream died?
+      const cudaError_t e = cudaStreamQuery(c.stream);
+      if (e != cudaSuccess && e != cudaErrorNotReady) throw CudaError(std::string("inner FGMRES: ") + cudaGetErrorString(e));
+      if (e == cudaSuccess && __atomic_load_n(&rec->seq, __ATOMIC_ACQUIRE) != c.fg_seq) throw CudaError("inner FGMRES: the device record never arrived");
+    }
+  }
+  return *rec;
+}
+void vec_scale_to_dev(Ctx &c, double *v, const double *x, const double *a, const int *gate, int64_t n) {
+  if (!n) return;
+  k_scale_to<<<vgrid(c, n), VT, 0, c.stream>>>(v, x, a, gate, n); LAUNCHED(c);
+}
+void vec_multi_add_dev(Ctx &c, double *x, const VecList &V, const double *coef, const int *count, int64_t n) {
+  if (!n) return;
+  k_multi_add<<<vgrid(c, n), VT, 0, c.stream>>>(x, V, coef, count, n); LAUNCHED(c);
+}
 
 void vec_copy(Ctx &c, double *y, const double *x, int64_t n) {
   if (!n || y == x) return;
@@ -242,7 +376,7 @@ void vec_multi_axpy_norm_dev(Ctx &c, int slot_norm, const VecList &V, int k, int
 
 static void ensure_red(Ctx &c) {
   if (!c.red_partial.p) {
-    c.red_partial.alloc((size_t)RED_MAX_BLOCKS * 32);
+    c.red_partial.alloc((size_t)std::max(RED_MAX_BLOCKS, c.num_sms * 8) * 32);
     c.red_result.alloc(RED_SLOTS);
     c.red_result.zero(c.stream);
     c.red_counter.alloc(1);

@@ -198,6 +198,93 @@ void solver_fgmres(Ctx &c, Control &ctl, const DOp &A, double *x, const double *
   if (state != SUCCESS) throw NoConvergence(accumulated_iterations, res, slot0 ? "inner FGMRES" : "FGMRES");
 }
 
+// Inner preconditioner of a device-driven FGMRES solve: a block-local sweep (fusable with the scaling of the next basis
+// vector and launchable behind the device-side verdict), or any other operator
+struct InnerM {
+  TriPlan *plan = nullptr;   // block-local SGS / ILU(0) plan, or null
+  bool sgs = false;
+  DOp op;                    // used when plan is null or not block-local
+  bool fusable() const { return plan && plan->nblk > 0; }
+};
+
+// SolverFGMRES::solve for the inner solves (max_basis_size = 30), recurrences on the device.  The host only launches: the
+// Hessenberg update, the residual estimate and SolverControl::check run in k_fg_step, whose verdict lands in a mapped host
+// record that the host polls (no stream synchronisation).  With a block-local sweep as the preconditioner the next
+// iteration's first kernel (scaling fused into the sweep) is already queued behind that verdict and skips itself if the
+// solve is over, so the GPU never waits for the host.
+void solver_fgmres_dev(Ctx &c, Control &ctl, const DOp &A, double *x, const double *b, const InnerM &M, Work &W, int slot0) {
+  const int basis_size = 30;
+  const int64_t n = W.n;
+  FgDev *st = fg_state(c);
+  double *aux = W.vec(0);
+  auto v = [&](int j) { return W.vec(1 + j); };
+  auto z = [&](int j) { return W.vec(1 + basis_size + j); };
+  for (int j = 0; j < basis_size; ++j) { v(j); z(j); }   // allocate before the first pointer is baked into a launch
+  aux = W.vec(0);
+  const double *slots = slot_ptr(c, slot0);
+  const int mode1 = c.ortho == 0 ? 0 : (c.ortho == 2 ? 1 : 3);
+  int it = 0;
+  double res = 0;
+  int gate = 0;
+  auto launch_M = [&](int j) {   // v_j = aux / a ; z_j = M^-1 v_j, both behind the device-side verdict
+    if (M.fusable()) {
+      if (M.sgs && M.plan->bl_sgs != 1) bl_refresh(c, *M.plan, true);
+      bl_sweep(c, *M.plan, M.sgs, z(j), aux, &st->a, v(j), &st->gate);
+    } else {
+      vec_scale_to_dev(c, v(j), aux, &st->a, &st->gate, n);
+      M.op(z(j), v(j));
+    }
+  };
+  do {
+    A(aux, x);
+    vec_sadd(c, aux, -1.0, 1.0, b, n);
+    vec_dot_dev(c, slot0 + 70, aux, aux, n);
+    fg_begin(c, slot_ptr(c, slot0 + 70), ctl.tol, ctl.max_steps, it);
+    const bool spec = M.fusable();
+    if (spec) launch_M(0);
+    FgRec r = fg_wait(c);
+    it = r.it; res = r.res; gate = r.gate;
+    if (gate == 2) break;
+    int j = 0;
+    for (; j < basis_size; ++j) {
+      if (!spec) launch_M(j);
+      A(aux, z(j));
+      VecList V;
+      for (int i = 0; i <= j; ++i) V.v[i] = v(i);
+      if (mode1 == 0) {
+        vec_dot_dev(c, slot0, aux, v(0), n);
+        for (int i = 1; i <= j; ++i) vec_add_and_dot_dev(c, slot0 + i, aux, -1.0, slot_ptr(c, slot0 + i - 1), v(i - 1), v(i), n);
+        vec_add_and_dot_dev(c, slot0 + j + 1, aux, -1.0, slot_ptr(c, slot0 + j), v(j), aux, n);
+      } else {
+        vec_multi_dot_dev(c, slot0, V, j + 1, aux, n);
+        vec_multi_axpy_norm_dev(c, slot0 + 64, V, j + 1, slot0, aux, n);
+        if (mode1 == 3) {
+          vec_multi_dot_dev(c, slot0 + 32, V, j + 1, aux, n);
+          vec_multi_axpy_norm_dev(c, slot0 + 65, V, j + 1, slot0 + 32, aux, n);
+        }
+      }
+      fg_step(c, slots, j, mode1);
+      if (spec && j + 1 < basis_size) launch_M(j + 1);
+      r = fg_wait(c);
+      if (r.gate == 1) {   // heavy cancellation in the first pass: orthogonalise again, then finish the step
+        vec_multi_dot_dev(c, slot0 + 32, V, j + 1, aux, n);
+        vec_multi_axpy_norm_dev(c, slot0 + 65, V, j + 1, slot0 + 32, aux, n);
+        fg_step(c, slots, j, 2);
+        if (spec && j + 1 < basis_size) launch_M(j + 1);   // the launch queued before saw gate 1 and skipped itself
+        r = fg_wait(c);
+      }
+      it = r.it; res = r.res; gate = r.gate;
+      if (gate != 0) break;
+    }
+    // x += sum_{m < ny} y_m z_m, count and coefficients on the device
+    VecList Z;
+    for (int i = 0; i < basis_size; ++i) Z.v[i] = z(i);
+    vec_multi_add_dev(c, x, Z, st->y, &st->ny, n);
+  } while (gate == 0);
+  ctl.last_step = it; ctl.last_value = res;
+  if (gate != 2) throw NoConvergence(it, res, "inner FGMRES");
+}
+
 // SolverGMRES::solve (max_n_tmp_vectors = 30, left preconditioning, preconditioned residual,
 // modified Gram-Schmidt with the re-orthogonalisation test every 5th step)
 void solver_gmres(Ctx &c, Control &ctl, const DOp &A, double *x, const double *b, const DOp &M, Work &W, int slot0) {
@@ -396,6 +483,14 @@ struct Preconditioner {
     c.tmp_p.alloc(c.nvec);
   }
 
+  // inner FGMRES on F: recurrences on the device unless NSX_OPT_HOST_INNER asks for the host-driven solver
+  void inner_fgmres(Control &ctl, double *x, const double *b, TriPlan *plan, bool sgs, const DOp &op, Work &W, int slot0) {
+    if (c.host_inner) { solver_fgmres(c, ctl, opF, x, b, op, W, slot0); return; }
+    InnerM M;
+    M.plan = plan; M.sgs = sgs; M.op = op;
+    solver_fgmres_dev(c, ctl, opF, x, b, M, W, slot0);
+  }
+
   void vmult(double *dst, const double *src) {
     const int64_t nu = c.n_u, np = c.n_p;
     const double *su = src, *sp = src + nu;
@@ -405,14 +500,14 @@ struct Preconditioner {
     c.stat_applies++;
     if (flavour == NSX_STATIONARY && type == 0) {  // NSSolverStationary.hpp:132-153
       Control cu(100001, 1e-1 * vec_norm(c, su, nu));
-      solver_fgmres(c, cu, opF, du, su, [&](double *y, const double *x) { sgs_apply(c, *F, y, x); }, WF, slot_inner);
+      inner_fgmres(cu, du, su, F, true, [&](double *y, const double *x) { sgs_apply(c, *F, y, x); }, WF, slot_inner);
       c.stat_inner_F += cu.last_step;
       Control cp(100000, 1e-1 * vec_norm(c, sp, np));
       solver_cg(c, cp, opM, dp, sp, [&](double *y, const double *x) { sgs_apply(c, *Mp, y, x); }, WP);
       c.stat_inner_S += cp.last_step;
     } else if (flavour == NSX_UNSTEADY && type == 0) {  // NSSolver.hpp:155-176
       Control cu(1000, 1e-1);
-      solver_fgmres(c, cu, opF, du, su, [&](double *y, const double *x) { ilu0_apply(c, *F, y, x); }, WF, slot_inner);
+      inner_fgmres(cu, du, su, F, false, [&](double *y, const double *x) { ilu0_apply(c, *F, y, x); }, WF, slot_inner);
       c.stat_inner_F += cu.last_step;
       Control cp(1000, 1e-1);
       solver_cg(c, cp, opM, dp, sp, [&](double *y, const double *x) { ilu0_apply(c, *Mp, y, x); }, WP);
@@ -420,8 +515,8 @@ struct Preconditioner {
     } else if (type == 1) {  // NSSolverStationary.hpp:190-218, NSSolver.hpp:212-237
       const bool st = flavour == NSX_STATIONARY;
       Control cu(st ? 10000001 : 2000001, (st ? 1e-2 : 1e-4) * vec_norm(c, su, nu));
-      if (st) solver_fgmres(c, cu, opF, du, su, [&](double *y, const double *x) { amg_apply(c, y, x); }, WF, slot_inner);
-      else solver_fgmres(c, cu, opF, du, su, [&](double *y, const double *x) { ilu0_apply(c, *F, y, x); }, WF, slot_inner);
+      if (st) inner_fgmres(cu, du, su, nullptr, false, [&](double *y, const double *x) { amg_apply(c, y, x); }, WF, slot_inner);
+      else inner_fgmres(cu, du, su, F, false, [&](double *y, const double *x) { ilu0_apply(c, *F, y, x); }, WF, slot_inner);
       c.stat_inner_F += cu.last_step;
       double *tmp = c.tmp_p.p;
       spmv(c, c.B, du, tmp);
@@ -431,7 +526,7 @@ struct Preconditioner {
       c.stat_inner_S += cp.last_step;
     } else if (flavour == NSX_STATIONARY) {  // aSIMPLE, NSSolverStationary.hpp:282-311
       Control cu(100000, 1e-1 * vec_norm(c, su, nu));
-      solver_fgmres(c, cu, opF, du, su, [&](double *y, const double *x) { ilu0_apply(c, *F, y, x); }, WF, slot_inner);
+      inner_fgmres(cu, du, su, F, false, [&](double *y, const double *x) { ilu0_apply(c, *F, y, x); }, WF, slot_inner);
       c.stat_inner_F += cu.last_step;
       double *tp = c.tmp_p.p, *tu = c.tmp_u.p, *delta_p = c.delta_p.p;
       spmv(c, c.B, du, tp);

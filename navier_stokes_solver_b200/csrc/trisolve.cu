@@ -461,11 +461,20 @@ TriPlan &tri_plan(Ctx &c, int block) {
   P.ordering = c.ordering;
   const int64_t n = A.nrows;
   P.n = n;
-  // owned range of each row; ghost columns (local ids >= n on a partitioned system) belong to no range, so
-  // the plan keeps exactly the rank-local diagonal block, as Ifpack does with overlap 0
+  // group of each row: couplings between rows of different groups are dropped.  Orderings 0 / 1: the owned ranges (the
+  // plan keeps exactly the rank-local diagonal block, as Ifpack does with overlap 0; ghost columns -- local ids >= n on a
+  // partitioned system -- belong to no group).  Ordering 2: every owned range is cut further into spatially compact
+  // blocks that one CTA sweeps out of shared memory (what the reference's preconditioners are under mpirun -n <#blocks>).
   std::vector<int32_t> range(std::max<int64_t>(n, A.ncols), -1);
-  for (size_t r = 0; r + 1 < owned.size(); ++r)
-    for (int64_t i = owned[r]; i < owned[r + 1]; ++i) range[i] = (int32_t)r;
+  if (c.ordering == 2) {
+    int ng = 0;
+    for (size_t r = 0; r + 1 < owned.size(); ++r)
+      if (owned[r + 1] > owned[r]) ng += geometric_blocks(c, block, A, owned[r], owned[r + 1], ng, range);
+    P.nblk = ng;
+  } else {
+    for (size_t r = 0; r + 1 < owned.size(); ++r)
+      for (int64_t i = owned[r]; i < owned[r + 1]; ++i) range[i] = (int32_t)r;
+  }
   // elimination order
   std::vector<int32_t> perm(n), iperm(n);
   if (c.ordering == 0) {
@@ -504,13 +513,31 @@ TriPlan &tri_plan(Ctx &c, int block) {
       }
       level[r] = m; nlev = std::max(nlev, m + 1);
     }
-    std::vector<int64_t> lp(nlev + 1, 0);
-    for (int64_t r = 0; r < n; ++r) lp[level[r] + 1]++;
-    for (int q = 0; q < nlev; ++q) lp[q + 1] += lp[q];
-    P.cptr = lp;
-    std::vector<int32_t> perm2(n);
-    for (int64_t r = 0; r < n; ++r) perm2[lp[level[r]]++] = perm[r];
-    perm.swap(perm2);
+    if (c.ordering == 1) {
+      std::vector<int64_t> lp(nlev + 1, 0);
+      for (int64_t r = 0; r < n; ++r) lp[level[r] + 1]++;
+      for (int q = 0; q < nlev; ++q) lp[q + 1] += lp[q];
+      P.cptr = lp;
+      std::vector<int32_t> perm2(n);
+      for (int64_t r = 0; r < n; ++r) perm2[lp[level[r]]++] = perm[r];
+      perm.swap(perm2);
+    } else {
+      // block-local: rows sorted by (block, level), the colour order breaking ties
+      std::vector<int64_t> key(n);
+      for (int64_t r = 0; r < n; ++r) key[r] = ((int64_t)range[perm[r]] * nlev + level[r]) * n + r;
+      std::sort(key.begin(), key.end());
+      std::vector<int32_t> perm2(n);
+      P.h_level.resize(n);
+      P.blk_off.assign(P.nblk + 1, 0);
+      for (int64_t q = 0; q < n; ++q) {
+        const int64_t r = key[q] % n;
+        perm2[q] = perm[r];
+        P.h_level[q] = level[r];
+        P.blk_off[range[perm[r]] + 1]++;
+      }
+      for (int b = 0; b < P.nblk; ++b) P.blk_off[b + 1] += P.blk_off[b];
+      perm.swap(perm2);
+    }
   }
   for (int64_t r = 0; r < n; ++r) iperm[perm[r]] = (int32_t)r;
   // permuted, filtered pattern
@@ -574,6 +601,7 @@ TriPlan &tri_plan(Ctx &c, int block) {
   P.val.alloc(P.nnz);
   P.work.alloc(n);
   P.yp.alloc(n);
+  if (P.nblk) bl_build(c, P);
   NSX_CUDA(cudaStreamSynchronize(c.stream));
   c.tri[block] = std::move(up);
   return *c.tri[block];
@@ -584,6 +612,7 @@ void tri_refresh_values(Ctx &c, TriPlan &P, const DevCSR &A) {
   k_gather_values<<<grid_for(P.nnz, 256, c.num_sms * 16), 256, 0, c.stream>>>(P.nnz, P.src.p, A.val.p, P.val.p);
   c.stat_launches++;
   P.factored = false;
+  P.bl_sgs = -1;
 }
 
 static TriArgs args_of(TriPlan &P, const double *x, double *y) {
@@ -607,10 +636,16 @@ void ilu0_factor(Ctx &c, TriPlan &P, const DevCSR &A) {
   }
   NSX_CUDA(cudaGetLastError());
   P.factored = true;
+  if (P.nblk) bl_refresh(c, P, false);
 }
 
 template <bool SGS>
 static void sweep(Ctx &c, TriPlan &P, double *y, const double *x) {
+  if (P.nblk) {
+    if (SGS && P.bl_sgs != 1) bl_refresh(c, P, true);
+    bl_sweep(c, P, SGS, y, x);
+    return;
+  }
   TriArgs T = args_of(P, x, y);
   const int nlf = (int)P.lvl_f.size() - 1, nlb = (int)P.lvl_b.size() - 1;
   if (c.coop_sweep == 1 && !P.cptr.empty() && P.cptr.size() <= 257) {

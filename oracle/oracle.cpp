@@ -771,11 +771,38 @@ static void solver_bicgstab(Control &ctl, const Op &A, Vec &x, const Vec &b, con
 // ---------------------------------------------------------------------------------------------
 struct LocalBlocks {
   std::vector<int64_t> off;  // nranks+1 row offsets; couplings across blocks are dropped
+  // Optional general form (the sub-blocks and elimination orders the product's sweeps may use): block b eliminates the
+  // rows ord[ord_off[b] .. ord_off[b+1]) in that sequence; blk[i] = block of row i; couplings between different blocks
+  // are dropped.  Empty = the contiguous ranges `off` in natural order (Ifpack's own behaviour).
+  const std::vector<int32_t> *ord = nullptr, *blk = nullptr;
+  const std::vector<int64_t> *ord_off = nullptr;
+  bool general() const { return ord && !ord->empty(); }
 };
 
 // Ifpack point relaxation, symmetric Gauss-Seidel, 1 sweep, omega 1, zero starting solution
 static void sgs_apply(const CSR &A, const LocalBlocks &lb, Vec &y, const Vec &x) {
   y.assign(x.size(), 0.0);
+  if (lb.general()) {
+    const std::vector<int32_t> &ord = *lb.ord, &blk = *lb.blk;
+    const int nb = (int)lb.ord_off->size() - 1;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < nb; ++b) {
+      const int64_t t0 = (*lb.ord_off)[b], t1 = (*lb.ord_off)[b + 1];
+      for (int pass = 0; pass < 2; ++pass)
+        for (int64_t t = pass == 0 ? t0 : t1 - 1; pass == 0 ? t < t1 : t >= t0; pass == 0 ? ++t : --t) {
+          const int64_t i = ord[t];
+          double dtemp = 0, dgl = 0;
+          for (int64_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
+            const int64_t c = A.col[k];
+            if (c >= A.nrows || blk[c] != b) continue;
+            if (c == i) dgl = A.val[k];
+            dtemp += A.val[k] * y[c];
+          }
+          y[i] += (x[i] - dtemp) / dgl;
+        }
+    }
+    return;
+  }
   const int nb = (int)lb.off.size() - 1;
 #pragma omp parallel for schedule(static, 1)
   for (int b = 0; b < nb; ++b) {
@@ -809,6 +836,54 @@ struct ILU0 {
   LocalBlocks lb;
   std::vector<double> lu;       // same pattern as A; entries coupling different blocks unused
   std::vector<int64_t> diag;    // position of the diagonal in each row
+  // general blocks / elimination orders: position of every row in its block's sequence, and per row its in-block
+  // entries sorted by that position (the order in which IKJ elimination visits them)
+  std::vector<int32_t> rank;
+  std::vector<int64_t> srt_ptr, srt;
+  void compute_general() {
+    const CSR &A_ = *A;
+    const int64_t n = A_.nrows;
+    const std::vector<int32_t> &ord = *lb.ord, &blk = *lb.blk;
+    rank.assign(n, 0);
+    for (int64_t t = 0; t < n; ++t) rank[ord[t]] = (int32_t)t;
+    srt_ptr.assign(n + 1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+      int64_t cnt = 0;
+      for (int64_t k = A_.rowptr[i]; k < A_.rowptr[i + 1]; ++k) cnt += A_.col[k] < n && blk[A_.col[k]] == blk[i];
+      srt_ptr[i + 1] = srt_ptr[i] + cnt;
+    }
+    srt.resize(srt_ptr[n]);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+      int64_t o = srt_ptr[i];
+      for (int64_t k = A_.rowptr[i]; k < A_.rowptr[i + 1]; ++k)
+        if (A_.col[k] < n && blk[A_.col[k]] == blk[i]) srt[o++] = k;
+      std::sort(srt.begin() + srt_ptr[i], srt.begin() + srt_ptr[i + 1], [&](int64_t a, int64_t b) { return rank[A_.col[a]] < rank[A_.col[b]]; });
+    }
+    const int nb = (int)lb.ord_off->size() - 1;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < nb; ++b) {
+      for (int64_t t = (*lb.ord_off)[b]; t < (*lb.ord_off)[b + 1]; ++t) {
+        const int64_t i = ord[t];
+        for (int64_t q = srt_ptr[i]; q < srt_ptr[i + 1]; ++q) {
+          const int64_t k = srt[q];
+          const int64_t kk = A_.col[k];
+          if (rank[kk] >= rank[i]) break;
+          const double lik = lu[k] / lu[diag[kk]];
+          lu[k] = lik;
+          // a_ij -= l_ik u_kj for the j behind k in row k that are also in row i (both lists ascend in rank)
+          int64_t qi = q + 1;
+          for (int64_t qk = srt_ptr[kk]; qk < srt_ptr[kk + 1]; ++qk) {
+            const int64_t m = srt[qk];
+            const int32_t rj = rank[A_.col[m]];
+            if (rj <= rank[kk]) continue;
+            while (qi < srt_ptr[i + 1] && rank[A_.col[srt[qi]]] < rj) ++qi;
+            if (qi < srt_ptr[i + 1] && A_.col[srt[qi]] == A_.col[m]) lu[srt[qi]] -= lik * lu[m];
+          }
+        }
+      }
+    }
+  }
   void compute(const CSR &A_, const LocalBlocks &lb_) {
     A = &A_; lb = lb_;
     lu = A_.val;
@@ -816,6 +891,7 @@ struct ILU0 {
     diag.assign(n, -1);
     for (int64_t i = 0; i < n; ++i)
       for (int64_t k = A_.rowptr[i]; k < A_.rowptr[i + 1]; ++k) if (A_.col[k] == i) diag[i] = k;
+    if (lb.general()) { compute_general(); return; }
     const int nb = (int)lb.off.size() - 1;
 #pragma omp parallel for schedule(static, 1)
     for (int b = 0; b < nb; ++b) {
@@ -848,6 +924,34 @@ struct ILU0 {
   }
   void apply(Vec &y, const Vec &x) const {
     y.resize(x.size());
+    if (lb.general()) {
+      const std::vector<int32_t> &ord = *lb.ord;
+      const int nb = (int)lb.ord_off->size() - 1;
+#pragma omp parallel for schedule(dynamic, 1)
+      for (int b = 0; b < nb; ++b) {
+        const int64_t t0 = (*lb.ord_off)[b], t1 = (*lb.ord_off)[b + 1];
+        for (int64_t t = t0; t < t1; ++t) {
+          const int64_t i = ord[t];
+          double s = x[i];
+          for (int64_t q = srt_ptr[i]; q < srt_ptr[i + 1]; ++q) {
+            const int64_t k = srt[q];
+            if (rank[A->col[k]] >= rank[i]) break;
+            s -= lu[k] * y[A->col[k]];
+          }
+          y[i] = s;
+        }
+        for (int64_t t = t1 - 1; t >= t0; --t) {
+          const int64_t i = ord[t];
+          double s = y[i];
+          for (int64_t q = srt_ptr[i]; q < srt_ptr[i + 1]; ++q) {
+            const int64_t k = srt[q];
+            if (rank[A->col[k]] > rank[i]) s -= lu[k] * y[A->col[k]];
+          }
+          y[i] = s / lu[diag[i]];
+        }
+      }
+      return;
+    }
     const int nb = (int)lb.off.size() - 1;
 #pragma omp parallel for schedule(static, 1)
     for (int b = 0; b < nb; ++b) {

@@ -36,6 +36,9 @@ struct Problem {
   std::vector<int> outlet_cell, outlet_face, cyl_cell, cyl_face;
   int nranks = 1;
   std::vector<int64_t> owned_u, owned_p;  // rank-local preconditioner blocks (Ifpack overlap 0)
+  // optional sub-blocks + elimination sequences of the ILU / SGS sweeps (index 0 velocity, 1 pressure): see LocalBlocks
+  std::vector<int32_t> ord[2], blk[2];
+  std::vector<int64_t> ord_off[2];
   // bookkeeping of the last solve
   long inner_F_iters = 0, inner_S_iters = 0, precond_applies = 0;
   double lift_force = 0, drag_force = 0;

@@ -31,6 +31,7 @@ def orc():
         L.orc_set_faces.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_set_dirichlet.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_set_ranks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_set_blocks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_vec.restype = C.c_void_p
         L.orc_vec.argtypes = [C.c_void_p, C.c_int]
         L.orc_block_values.restype = C.c_void_p
@@ -83,6 +84,17 @@ class Oracle:
         L.orc_set_dirichlet(self.h, len(self.bc_dof), ptr(self.bc_dof), ptr(self.bc_val))
         ou, op = disc.array("OWNED_U"), disc.array("OWNED_P")
         L.orc_set_ranks(self.h, disc.nranks, ptr(ou), ptr(op))
+
+    def set_blocks(self, which, ord_off=None, order=None):
+        """Sub-blocks + elimination sequences of the ILU / SGS sweeps (which: 0 velocity rows, 1 pressure rows)."""
+        if ord_off is None:
+            rc = orc().orc_set_blocks(self.h, which, 0, None, None)
+        else:
+            ord_off = np.ascontiguousarray(ord_off, dtype=np.int64)
+            order = np.ascontiguousarray(order, dtype=np.int32)
+            rc = orc().orc_set_blocks(self.h, which, len(ord_off) - 1, ptr(ord_off), ptr(order))
+        if rc:
+            raise ValueError("orc_set_blocks: the sequences must cover every row exactly once")
 
     def vec(self, which):
         p = orc().orc_vec(self.h, which)

@@ -80,18 +80,80 @@ def test_schur_complement(setup):
     assert np.abs(S_d.toarray() - ref).max() <= 1e-12 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("ordering", [0, 1])
+def use_block_local(dev, rows):
+    dev.set_option(N.OPT_BLOCK_ROWS, rows)
+    dev.set_option(N.OPT_ORDERING, 2)
+
+
+def mirror_blocks(dev, orc):
+    """hands the device's sweep blocks + elimination sequences to the oracle (both row sets)"""
+    out = {}
+    for which, block in ((0, N.BLOCK_F), (1, N.BLOCK_MP)):
+        off, perm = dev.sweep_blocks(block)
+        orc.set_blocks(which, off, perm)
+        out[block] = (off, perm)
+    return out
+
+
+@pytest.mark.parametrize("rows", [64, 300])
+@pytest.mark.parametrize("block,kind", [(N.BLOCK_F, 0), (N.BLOCK_F, 1), (N.BLOCK_MP, 0), (N.BLOCK_MP, 1)])
+def test_block_local_sweeps_match_oracle(setup, rows, block, kind):
+    """Elimination order 2 (the default): the owned rows cut into spatially compact blocks, one CTA each, multicolour
+    inside a block, couplings between blocks dropped -- against the oracle's Ifpack restatement given the same blocks and
+    the same sequences (Ifpack's overlap-0 semantics at one rank per block)."""
+    d, orc, dev = setup
+    use_block_local(dev, rows)
+    try:
+        blocks = mirror_blocks(dev, orc)
+        off, perm = blocks[block]
+        n = d.n_u if block == N.BLOCK_F else d.n_p
+        assert len(off) - 1 >= 2 and off[0] == 0 and off[-1] == n and (np.diff(off) > 0).all()
+        assert sorted(perm.tolist()) == list(range(n))
+        x = np.random.default_rng(11).uniform(-1, 1, n)
+        if kind == 1:
+            lu_d, _ = dev.ilu0_factor(block)
+            lu_o = orc.ilu0_factor(block)
+            # entries that couple two blocks are dropped on the device (0) and left untouched by the oracle: compare the kept ones
+            rp, col = d.pattern("F" if block == N.BLOCK_F else "MP")
+            blk = np.empty(n, dtype=np.int64)
+            for b in range(len(off) - 1):
+                blk[perm[off[b]:off[b + 1]]] = b
+            rows_of = np.repeat(np.arange(n), np.diff(rp))
+            kept = blk[rows_of] == blk[col]
+            assert kept.sum() < len(col)   # something was dropped
+            assert rel(lu_d[kept], lu_o[kept]) < 1e-11
+            assert (lu_d[~kept] == 0).all()
+        y_d, y_o = dev.inner_apply(block, kind, x), orc.inner_apply(block, kind, x)
+        assert rel(y_d, y_o) < 1e-11
+        for _ in range(3):   # same bits from one application to the next
+            np.testing.assert_array_equal(dev.inner_apply(block, kind, x), y_d)
+    finally:
+        orc.set_blocks(0); orc.set_blocks(1)
+        dev.set_option(N.OPT_BLOCK_ROWS, 0)
+        dev.set_option(N.OPT_ORDERING, 0)
+
+
+@pytest.mark.parametrize("ordering", [0, 1, 2])
 @pytest.mark.parametrize("block,kind", [(N.BLOCK_F, 0), (N.BLOCK_F, 1), (N.BLOCK_MP, 0), (N.BLOCK_MP, 1)])
 def test_inner_preconditioners_by_definition(setup, ordering, block, kind):
-    """Both elimination orders against a dense restatement of the definition on the permuted matrix:
-    SGS = (D+U)^-1 D (D+L)^-1, ILU(0) = the incomplete factors restricted to the pattern."""
+    """All elimination orders against a dense restatement of the definition on the permuted matrix:
+    SGS = (D+U)^-1 D (D+L)^-1, ILU(0) = the incomplete factors restricted to the pattern; order 2 on the block-diagonal
+    part of the matrix (couplings between two sweep blocks dropped)."""
     d, orc, dev = setup
+    if ordering == 2:
+        dev.set_option(N.OPT_BLOCK_ROWS, 200)
     dev.set_option(N.OPT_ORDERING, ordering)
     try:
         A = orc.csr(block).toarray()
         n = A.shape[0]
         perm = dev.ordering(block)
         assert sorted(perm.tolist()) == list(range(n))
+        if ordering == 2:
+            off, _ = dev.sweep_blocks(block)
+            blk = np.empty(n, dtype=np.int64)
+            for b in range(len(off) - 1):
+                blk[perm[off[b]:off[b + 1]]] = b
+            A = A * (blk[:, None] == blk[None, :])
         Ap = A[np.ix_(perm, perm)]
         x = np.random.default_rng(3).uniform(-1, 1, n)
         y = dev.inner_apply(block, kind, x)
@@ -113,9 +175,10 @@ def test_inner_preconditioners_by_definition(setup, ordering, block, kind):
         ref = np.empty(n)
         ref[perm] = yp
         assert rel(y, ref) < 1e-9
-        if ordering == 1:
+        if ordering >= 1:
             assert dev.stat("LEVELS_F" if block == N.BLOCK_F else "LEVELS_MP") < 200
     finally:
+        dev.set_option(N.OPT_BLOCK_ROWS, 0)
         dev.set_option(N.OPT_ORDERING, 0)
 
 
