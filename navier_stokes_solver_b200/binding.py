@@ -7,6 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIBNSX = os.environ.get("NSX_LIB") or os.path.join(ROOT, "navier_stokes_solver_b200", "libnsx.so")
+LIBNSX_HOST = os.environ.get("NSX_HOST_LIB") or os.path.join(ROOT, "navier_stokes_solver_b200", "libnsx_host.so")
 
 c_i64p = C.POINTER(C.c_int64)
 c_dp = C.POINTER(C.c_double)
@@ -45,15 +46,16 @@ NSX_HOST_SYMBOLS = ["nsx_disc_generate", "nsx_disc_from_gmsh", "nsx_disc_local",
                     "nsx_disc_array", "nsx_disc_inlet_values"]
 
 _nsx = None
+_nsx_host = None
 
 
-def nsx():
-    """The product library.  Loading works without a GPU; compute calls need one."""
-    global _nsx
-    if _nsx is None:
-        if not os.path.exists(LIBNSX):
-            raise RuntimeError(f"{LIBNSX} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
-        L = C.CDLL(LIBNSX)
+def nsx_host():
+    """The host set-up stand-in (include/nsx_host.h): plain C++, no CUDA, never loads the device library."""
+    global _nsx_host
+    if _nsx_host is None:
+        if not os.path.exists(LIBNSX_HOST):
+            raise RuntimeError(f"{LIBNSX_HOST} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIBNSX_HOST)
         L.nsx_disc_generate.restype = C.c_void_p
         L.nsx_disc_generate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
         L.nsx_disc_from_gmsh.restype = C.c_void_p
@@ -67,6 +69,17 @@ def nsx():
         L.nsx_disc_array.argtypes = [C.c_void_p, C.c_int, c_i64p]
         L.nsx_disc_inlet_values.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.nsx_host_last_error.restype = C.c_char_p
+        _nsx_host = L
+    return _nsx_host
+
+
+def nsx():
+    """The product library (include/nsx.h).  Loading works without a GPU; compute calls need one."""
+    global _nsx
+    if _nsx is None:
+        if not os.path.exists(LIBNSX):
+            raise RuntimeError(f"{LIBNSX} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIBNSX)
         vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
         L.nsx_create.argtypes = [i32, i32, i32, vp, C.POINTER(vp)]
         L.nsx_destroy.argtypes = [vp]
@@ -125,9 +138,9 @@ class Disc:
 
     def __init__(self, handle):
         if not handle:
-            raise RuntimeError(nsx().nsx_host_last_error().decode())
+            raise RuntimeError(nsx_host().nsx_host_last_error().decode())
         self.h = handle
-        L = nsx()
+        L = nsx_host()
         for k, v in DI.items():
             setattr(self, k.lower(), int(L.nsx_disc_info(self.h, v)))
         self.n = self.n_u + self.n_p
@@ -135,7 +148,7 @@ class Disc:
 
     def local(self, rank):
         """This rank's share (own cells + ghost layer, local numbering, owned-row patterns, halo plans)."""
-        return Disc(nsx().nsx_disc_local(self.h, rank))
+        return Disc(nsx_host().nsx_disc_local(self.h, rank))
 
     def owned_global_ids(self):
         """Global block-vector positions [velocity | pressure] of a local view's owned entries (n_u_global needed
@@ -155,16 +168,16 @@ class Disc:
 
     @classmethod
     def generate(cls, nx, ny, triangles=False, nranks=1):
-        return cls(nsx().nsx_disc_generate(nx, ny, int(triangles), nranks))
+        return cls(nsx_host().nsx_disc_generate(nx, ny, int(triangles), nranks))
 
     @classmethod
     def from_gmsh(cls, path, nranks=1):
-        return cls(nsx().nsx_disc_from_gmsh(path.encode(), nranks))
+        return cls(nsx_host().nsx_disc_from_gmsh(path.encode(), nranks))
 
     def array(self, name):
         code, dt = DA[name]
         cnt = C.c_int64()
-        p = nsx().nsx_disc_array(self.h, code, C.byref(cnt))
+        p = nsx_host().nsx_disc_array(self.h, code, C.byref(cnt))
         if cnt.value == 0:
             return np.zeros(0, dtype=dt)
         buf = (C.c_char * (cnt.value * np.dtype(dt).itemsize)).from_address(p)
@@ -172,7 +185,7 @@ class Disc:
 
     def inlet_values(self, amplitude):
         v = np.zeros(self.nbc)
-        nsx().nsx_disc_inlet_values(self.h, amplitude, ptr(v))
+        nsx_host().nsx_disc_inlet_values(self.h, amplitude, ptr(v))
         return v
 
     def pattern(self, name):
@@ -180,7 +193,7 @@ class Disc:
 
     def __del__(self):
         try:
-            nsx().nsx_disc_free(self.h)
+            nsx_host().nsx_disc_free(self.h)
         except Exception:
             pass
 

@@ -127,10 +127,10 @@ struct TriPlan {
   DevBuf<double> bl_val;                // value sections of all passes (ELL slices + reciprocal diagonals)
   DevBuf<uint16_t> bl_idx;              // index sections (block-local columns + row slots)
   DevBuf<int64_t> bl_map;               // per entry of bl_val: (index into val << 2) | kind
-  DevBuf<int4> bl_pass;                 // pass headers
+  DevBuf<unsigned char> bl_pass;        // pass headers (sweep_block.cu PassHdr)
   DevBuf<BlkDesc> bl_blk;               // block descriptors
   int64_t bl_nval = 0;
-  int bl_max_rows = 0, bl_max_pass = 0, bl_stage_val = 0, bl_stage_idx = 0;   // sizes of the shared-memory areas (elements)
+  int bl_max_rows = 0, bl_max_pass = 0, bl_ring = 0;   // sizes of the shared-memory areas (rows, passes, ring bytes)
   int bl_sgs = -1;                      // what the stream currently holds: 1 SGS values, 0 ILU factors, -1 nothing
 };
 

@@ -9,13 +9,17 @@
 // ONE CTA owns a block for the whole application:
 //   * the block's slice of the work vector (<= 8192 rows = 64 KB) lives in shared memory, so the dependent gathers of a
 //     sweep never leave the SM and a dependency level costs one __syncthreads instead of a grid-wide barrier;
-//   * rows inside a block follow a multicolour order re-sorted by dependency level (32 levels for Q3/Q2); a level is cut
-//     into "passes" of up to NT / lanes rows, 4 .. 32 lanes per row depending on the row length;
-//   * the matrix is stored per pass as an ELL slice [entry quad][row slot][lane] of FP64 values + 16-bit block-local
-//     columns, followed by the reciprocal diagonals and the row slots -- 10 bytes per non-zero, each pass one
-//     contiguous span that the TMA engine (cp.async.bulk completing on an mbarrier) brings into a 4-stage ring while
-//     earlier passes compute.  The lower sweep streams the strictly lower entries, the upper sweep the strictly upper
-//     ones: every stored non-zero of the block-diagonal part crosses HBM exactly once per application.
+//   * rows inside a block follow a multicolour order re-sorted by dependency level (32 levels for Q3/Q2); a level is one
+//     or a few "passes" of up to 512 lanes, a row owning ceil(entries / Q) consecutive lanes of a warp (Q = 4 entries per
+//     lane), reduced by a segmented shuffle reduction; only the end of a level costs a barrier, and only among the 16
+//     consumer warps of the CTA (bar.sync);
+//   * the matrix is stored per pass as FP64 values + 16-bit block-local columns, lane-major, followed by the reciprocal
+//     diagonals, the lane descriptors and the row slots (about 12 bytes per non-zero including the padding), each pass
+//     two contiguous spans that a producer warp brings into a shared-memory ring with the TMA engine (cp.async.bulk
+//     completing on an mbarrier), up to 16 passes ahead of the consumers; ring offsets and the pass whose consumption
+//     frees each region are fixed by the host when the plan is built.  The lower sweep streams the strictly lower
+//     entries, the upper sweep the strictly upper ones: every stored non-zero of the block-diagonal part crosses HBM
+//     exactly once per application.
 // The reciprocal of the diagonal is stored (one rounding away from the division the CPU oracle does).
 #include <algorithm>
 #include <numeric>
@@ -27,99 +31,110 @@ namespace nsx {
 
 namespace {
 
-constexpr int NT = 512;           // threads per CTA
-constexpr int NSTAGE = 4;         // ring stages
-constexpr int PASS_ENTRIES = 4096;  // matrix entries per pass at most (values 32 KB + columns 8 KB)
+constexpr int NC = 512;           // consumer threads (16 warps); one more warp feeds the ring
+constexpr int NT = NC + 32;
+constexpr int NSLOT = 16;         // passes in flight at most (full / empty barrier pairs)
 constexpr int MAX_BLOCK_ROWS = 8192;
+constexpr int PASS_BYTES_MAX = 40 * 1024;
 
-// pass header: x = offset of the value section (doubles, from the block's val_base), y = offset of the index section
-// (uint16 units, from idx_base), z = rows (padded to 8) | quads << 16, w = log2(lanes) | backward << 8
-__device__ __forceinline__ int hdr_rows(const int4 &h) { return h.z & 0xffff; }
-__device__ __forceinline__ int hdr_quads(const int4 &h) { return (h.z >> 16) & 0xffff; }
-__device__ __forceinline__ int hdr_llog(const int4 &h) { return h.w & 0xff; }
-__device__ __forceinline__ int hdr_bwd(const int4 &h) { return (h.w >> 8) & 1; }
+// Pass format ("lane-split rows"): a row with c entries in this sweep's triangle owns k = max(1, ceil(c / Q)) consecutive
+// lanes of one warp, Q entries each; rows are packed into warps first-fit.  With T = 32 x warps lanes in the pass:
+//   value section : val[Q][T] (entry q of lane t at q T + t), then rdiag[rows]           (doubles)
+//   index section : col[Q][T], meta[T], rowid[rows]                                        (uint16)
+//   meta: bit 15 = first lane of its row, bits 14..5 = row slot in the pass, bits 4..0 = lanes of the row behind this one
+// Header (two int4): {value offset, index offset (elements, from the block's bases), ring offset / 16, pass to wait for}
+//                    {T | Q << 16, rows | rounds << 16 | flags << 24, value count, index count}; flags: 1 upper sweep, 2 level ends
+struct PassHdr { int val_off, idx_off, ring16, wait; int tq, rrf, val_cnt, idx_cnt; };
 
 template <bool SGS>
-__global__ void __launch_bounds__(NT, 1) k_sweep_block(const BlkDesc *__restrict__ blks, const int4 *__restrict__ passes, const double *__restrict__ bl_val,
+__global__ void __launch_bounds__(NT, 1) k_sweep_block(const BlkDesc *__restrict__ blks, const PassHdr *__restrict__ passes, const double *__restrict__ bl_val,
                                                         const uint16_t *__restrict__ bl_idx, const int32_t *__restrict__ perm, const double *__restrict__ x,
                                                         double *__restrict__ y, const double *__restrict__ scale, double *__restrict__ v_out,
-                                                        const int *__restrict__ gate, int max_rows, int max_pass, int stage_val, int stage_idx) {
+                                                        const int *__restrict__ gate, int max_rows, int max_pass, int ring_bytes) {
   if (gate && *gate != 0) return;
   extern __shared__ __align__(128) unsigned char smem[];
-  // layout: stages (values then indices, each 128-byte aligned), work vector, pass headers, barriers
-  const size_t stage_bytes = (size_t)stage_val * 8 + (size_t)stage_idx * 2;
-  double *xs = reinterpret_cast<double *>(smem + NSTAGE * stage_bytes);
-  int4 *hdr = reinterpret_cast<int4 *>(xs + max_rows + 8);
-  uint64_t *full = reinterpret_cast<uint64_t *>(hdr + max_pass);
+  // layout: ring, work vector (+ 8 zero slots for padding rows / entries), pass headers, barriers
+  double *xs = reinterpret_cast<double *>(smem + ring_bytes);
+  PassHdr *hdr = reinterpret_cast<PassHdr *>(xs + max_rows + 8);
+  uint64_t *full = reinterpret_cast<uint64_t *>(hdr + max_pass), *empty = full + NSLOT;
   const BlkDesc B = blks[blockIdx.x];
   const int tid = threadIdx.x;
-  const double *gval = bl_val + B.val_base;
-  const uint16_t *gidx = bl_idx + B.idx_base;
-  auto issue = [&](int p) {  // thread 0: bulk copies of pass p into its stage
-    const int4 h = hdr[p];
-    const int st = p % NSTAGE;
-    const uint32_t cnt = (uint32_t)hdr_quads(h) * hdr_rows(h) * (1u << hdr_llog(h)) + hdr_rows(h);
-    unsigned char *dst = smem + st * stage_bytes;
-    mbar_expect_tx(&full[st], cnt * 10u);
-    bulk_g2s(dst, gval + (uint32_t)h.x, cnt * 8u, &full[st]);
-    bulk_g2s(dst + (size_t)stage_val * 8, gidx + (uint32_t)h.y, cnt * 2u, &full[st]);
-  };
   for (int p = tid; p < B.npass; p += NT) hdr[p] = passes[B.pass0 + p];
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NC / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-  if (tid == 0)
-    for (int p = 0; p < NSTAGE && p < B.npass; ++p) issue(p);
   // right-hand side of the block into shared memory (optionally scaled: v = x / *scale, also stored for the Krylov basis)
   {
-    const double inv = scale ? 1.0 / *scale : 1.0;
+    double inv = 1.0;
+    if (scale) { const double a = *scale; inv = isfinite(a) ? 1.0 / a : 0.0; }
     for (int i = tid; i < B.nrows; i += NT) {
       const int32_t g = perm[B.row0 + i];
       double v = x[g];
-      if (scale) { v *= inv; v_out[g] = v; }
+      if (scale) { v = inv * v; v_out[g] = v; }
       xs[i] = v;
     }
-    if (tid < 8) xs[max_rows + tid] = 0.0;  // slot of the padding rows / padding entries
+    if (tid < 8) xs[max_rows + tid] = 0.0;
   }
   __syncthreads();
+  if (tid >= NC) {
+    // producer warp: one lane walks the passes; a pass is issued as soon as the ring region the host assigned to it is free
+    if (tid == NC) {
+      const double *gval = bl_val + B.val_base;
+      const uint16_t *gidx = bl_idx + B.idx_base;
+      for (int p = 0; p < B.npass; ++p) {
+        const PassHdr h = hdr[p];
+        if (h.wait >= 0) mbar_wait(&empty[h.wait % NSLOT], (h.wait / NSLOT) & 1);
+        const int st = p % NSLOT;
+        unsigned char *dst = smem + (size_t)h.ring16 * 16;
+        mbar_expect_tx(&full[st], (uint32_t)h.val_cnt * 8u + (uint32_t)h.idx_cnt * 2u);
+        bulk_g2s(dst, gval + (uint32_t)h.val_off, (uint32_t)h.val_cnt * 8u, &full[st]);
+        bulk_g2s(dst + (size_t)h.val_cnt * 8, gidx + (uint32_t)h.idx_off, (uint32_t)h.idx_cnt * 2u, &full[st]);
+      }
+    }
+    return;
+  }
+  const int lane = tid & 31;
   for (int p = 0; p < B.npass; ++p) {
-    const int4 h = hdr[p];
-    const int st = p % NSTAGE;
-    const int rows = hdr_rows(h), quads = hdr_quads(h), llog = hdr_llog(h);
-    const double *sv = reinterpret_cast<const double *>(smem + st * stage_bytes);
-    const uint16_t *sc = reinterpret_cast<const uint16_t *>(smem + st * stage_bytes + (size_t)stage_val * 8);
-    mbar_wait(&full[st], (p / NSTAGE) & 1);
-    const int slot = tid >> llog, lane = tid & ((1 << llog) - 1);
-    const int stride = rows << llog;   // entries per quad
-    const bool active = slot < rows;
-    double a0 = 0, a1 = 0;
-    if (active) {
+    const PassHdr h = hdr[p];
+    const int st = p % NSLOT;
+    const int T = h.tq & 0xffff, Q = h.tq >> 16;
+    const int rows = h.rrf & 0xffff, rounds = (h.rrf >> 16) & 0xff, flags = h.rrf >> 24;
+    mbar_wait(&full[st], (p / NSLOT) & 1);   // every warp, also the idle ones: nobody runs more than NSLOT passes ahead
+    if (tid < T) {   // warp-uniform: T is a multiple of 32
+      const double *sv = reinterpret_cast<const double *>(smem + (size_t)h.ring16 * 16);
+      const uint16_t *sc = reinterpret_cast<const uint16_t *>(sv + h.val_cnt);
+      double a0 = 0, a1 = 0;
       int q = 0;
-      for (; q + 1 < quads; q += 2) {
-        const int i0 = q * stride + tid, i1 = i0 + stride;
+      for (; q + 1 < Q; q += 2) {
+        const int i0 = q * T + tid, i1 = i0 + T;
         const double v0 = sv[i0], v1 = sv[i1];
         const int c0 = sc[i0], c1 = sc[i1];
         a0 = fma(v0, xs[c0], a0);
         a1 = fma(v1, xs[c1], a1);
       }
-      if (q < quads) { const int i0 = q * stride + tid; a0 = fma(sv[i0], xs[sc[i0]], a0); }
+      if (q < Q) { const int i0 = q * T + tid; a0 = fma(sv[i0], xs[sc[i0]], a0); }
+      double s = a0 + a1;
+      const int m = sc[Q * T + tid];
+      const int behind = m & 31;
+      for (int r = 0, o = 1; r < rounds; ++r, o <<= 1) {   // segmented reduction: the first lane of a row collects its lanes
+        const double up = __shfl_down_sync(0xffffffffu, s, o);
+        if (o <= behind) s += up;
+      }
+      if (m & 0x8000) {
+        const int slot = (m >> 5) & 0x3ff;
+        const int row = sc[Q * T + T + slot];
+        const double rdiag = sv[Q * T + slot];
+        const double r0 = xs[row];
+        if (!(flags & 1)) xs[row] = (r0 - s) * rdiag;            // w = (D + L)^-1 x   |  w = L^-1 x (rdiag = 1)
+        else xs[row] = SGS ? r0 - s * rdiag : (r0 - s) * rdiag;  // y = w - D^-1 U y   |  y = U^-1 w
+      }
     }
-    double s = a0 + a1;
-    for (int o = (1 << llog) >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (active && lane == 0) {
-      const int tail = quads * stride;
-      const int row = sc[tail + slot];
-      const double dinv = sv[tail + slot];
-      const double r = xs[row];
-      if (!hdr_bwd(h)) xs[row] = (r - s) * dinv;            // w = (D + L)^-1 x   |  w = L^-1 x (dinv = 1)
-      else xs[row] = SGS ? r - s * dinv : (r - s) * dinv;   // y = w - D^-1 U y   |  y = U^-1 w
-    }
-    __syncthreads();   // the level's results are visible, the stage is free
-    if (tid == 0 && p + NSTAGE < B.npass) issue(p + NSTAGE);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);   // this warp has finished reading the pass
+    if (flags & 2) asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");   // the level's results are visible to the next level
   }
-  for (int i = tid; i < B.nrows; i += NT) y[perm[B.row0 + i]] = xs[i];
+  for (int i = tid; i < B.nrows; i += NC) y[perm[B.row0 + i]] = xs[i];
 }
 
 // kind (low 2 bits of the map): 0 value, 1 zero, 2 reciprocal diagonal of a lower-sweep pass, 3 of an upper-sweep pass
@@ -193,18 +208,28 @@ int geometric_blocks(Ctx &c, int block, const DevCSR &A, int64_t lo, int64_t hi,
     const double m = cnt[i] ? 1.0 / cnt[i] : 0.0;
     pts[i] = Pt{sx[i] * m, sy[i] * m, (double)(A.h_rowptr[lo + i + 1] - A.h_rowptr[lo + i]), (int32_t)(lo + i)};
   }
-  int64_t target = c.block_rows > 0 ? c.block_rows : std::max<int64_t>(512, std::min<int64_t>(4096, n / std::max(1, c.num_sms)));
-  target = std::min<int64_t>(target, MAX_BLOCK_ROWS / 2);   // weights are non-zero counts: leave room for blocks of short rows
-  int64_t parts = std::max<int64_t>(1, (n + target - 1) / target);
-  if (parts > c.num_sms && c.block_rows <= 0) parts = (parts + c.num_sms - 1) / c.num_sms * c.num_sms;   // whole waves
+  // one block per SM while that gives blocks of 512 .. 4096 rows; fewer blocks below, whole waves of blocks above (the
+  // weights are non-zero counts, so a block of short rows may hold more rows than the average: MAX_BLOCK_ROWS leaves room)
+  int64_t parts;
+  if (c.block_rows > 0) parts = (n + c.block_rows - 1) / c.block_rows;
+  else {
+    const int64_t per = n / std::max(1, c.num_sms);
+    if (per <= 512) parts = std::min<int64_t>(c.num_sms, (n + 256) / 512);
+    else parts = (int64_t)c.num_sms * ((per + 4095) / 4096);
+  }
+  parts = std::max<int64_t>(1, parts);
   rcb(pts, 0, n, (int)parts, first_group, grp);
   return (int)parts;
+}
+
+static size_t bl_fixed_smem(int max_rows, int max_pass) {
+  return (size_t)(max_rows + 8) * 8 + (size_t)max_pass * sizeof(PassHdr) + 2 * NSLOT * 8;
 }
 
 void bl_build(Ctx &c, TriPlan &P) {
   const int nb = P.nblk;
   std::vector<BlkDesc> blk(nb);
-  std::vector<std::vector<int4>> pass(nb);
+  std::vector<std::vector<PassHdr>> pass(nb);
   std::vector<std::vector<int64_t>> vmap(nb);
   std::vector<std::vector<uint16_t>> idx(nb);
   int max_rows = 0;
@@ -216,79 +241,132 @@ void bl_build(Ctx &c, TriPlan &P) {
 #pragma omp parallel for schedule(dynamic, 1)
   for (int b = 0; b < nb; ++b) {
     const int64_t r0 = P.blk_off[b], r1 = P.blk_off[b + 1];
-    std::vector<int4> &ps = pass[b];
+    std::vector<PassHdr> &ps = pass[b];
     std::vector<int64_t> &vm = vmap[b];
     std::vector<uint16_t> &ix = idx[b];
     std::vector<int64_t> rows;
+    struct Seg { int64_t row; int lane0, k; };
+    std::vector<Seg> segs;
+    std::vector<int> room;   // free lanes per warp of the pass under construction
     for (int dir = 0; dir < 2; ++dir) {
-      // levels ascending for the lower sweep, descending for the upper one; rows of a level are contiguous
+      // levels ascending for the lower sweep, descending for the upper one; the rows of a level are contiguous
       int64_t a = dir == 0 ? r0 : r1;
       while (dir == 0 ? a < r1 : a > r0) {
-        int64_t e;
-        if (dir == 0) { e = a; while (e < r1 && P.h_level[e] == P.h_level[a]) ++e; }
-        else { e = a; while (e > r0 && P.h_level[e - 1] == P.h_level[a - 1]) --e; }
+        int64_t e = a;
+        if (dir == 0) { while (e < r1 && P.h_level[e] == P.h_level[a]) ++e; }
+        else { while (e > r0 && P.h_level[e - 1] == P.h_level[a - 1]) --e; }
         const int64_t lo = std::min(a, e), hi = std::max(a, e);
         auto count = [&](int64_t r) -> int { return dir == 0 ? P.h_diag[r] : (int)(P.h_rowptr[r + 1] - P.h_rowptr[r]) - P.h_diag[r] - 1; };
         rows.resize(hi - lo);
         std::iota(rows.begin(), rows.end(), lo);
         std::stable_sort(rows.begin(), rows.end(), [&](int64_t u, int64_t v) { return count(u) > count(v); });
+        const int maxc = rows.empty() ? 0 : count(rows[0]);
+        int Q = 4;
+        while (Q * 32 < maxc) Q *= 2;   // a row's lanes stay inside one warp
+        if (maxc == 0) Q = 1;
         size_t at = 0;
         while (at < rows.size()) {
-          const int W = count(rows[at]);
-          const int llog = W <= 24 ? 2 : W <= 48 ? 3 : W <= 96 ? 4 : 5;
-          const int lanes = 1 << llog, quads = (W + lanes - 1) / lanes;
-          int cap = NT / lanes;
-          if (quads) cap = std::min(cap, PASS_ENTRIES / (quads * lanes) / 8 * 8);
-          if (cap < 8) {
+          // first-fit packing of the rows' lane groups into the warps of one pass
+          segs.clear(); room.clear();
+          int maxk = 1;
+          size_t next = at;
+          for (; next < rows.size(); ++next) {
+            const int k = std::max(1, (count(rows[next]) + Q - 1) / Q);
+            int w = 0;
+            while (w < (int)room.size() && room[w] < k) ++w;
+            if (w == (int)room.size()) {
+              if ((int)room.size() == NC / 32) break;
+              room.push_back(32);
+            }
+            segs.push_back(Seg{rows[next], w * 32 + (32 - room[w]), k});
+            room[w] -= k;
+            maxk = std::max(maxk, k);
+          }
+          const int T = 32 * (int)room.size(), nr = (int)segs.size(), nrp = (nr + 7) / 8 * 8;
+          int rounds = 0;
+          while ((1 << rounds) < maxk) ++rounds;
+          PassHdr h;
+          h.val_off = (int)vm.size(); h.idx_off = (int)ix.size(); h.ring16 = 0; h.wait = -1;
+          h.tq = T | (Q << 16);
+          h.rrf = nrp | (rounds << 16) | ((dir | (next == rows.size() ? 2 : 0)) << 24);
+          h.val_cnt = Q * T + nrp; h.idx_cnt = Q * T + T + nrp;
+          if ((size_t)h.val_cnt * 8 + (size_t)h.idx_cnt * 2 > (size_t)PASS_BYTES_MAX) {
 #pragma omp critical
-            err = "block-local sweep: a matrix row is too long for one pass";
-            cap = 8;
+            err = "block-local sweep: a pass exceeds the ring";
           }
-          const int nr = (int)std::min<size_t>(cap, rows.size() - at);
-          const int nrp = (nr + 7) / 8 * 8;
-          int4 h;
-          h.x = (int)vm.size(); h.y = (int)ix.size();
-          h.z = nrp | (quads << 16); h.w = llog | (dir << 8);
           ps.push_back(h);
-          for (int q = 0; q < quads; ++q)
-            for (int s = 0; s < nrp; ++s)
-              for (int l = 0; l < lanes; ++l) {
-                const int e2 = q * lanes + l;
-                if (s < nr && e2 < count(rows[at + s])) {
-                  const int64_t r = rows[at + s];
-                  const int64_t k = P.h_rowptr[r] + (dir == 0 ? e2 : P.h_diag[r] + 1 + e2);
-                  vm.push_back(k << 2);
-                  ix.push_back((uint16_t)(P.h_col[k] - r0));
-                } else { vm.push_back(1); ix.push_back((uint16_t)dummy); }
+          const size_t v0 = vm.size(), i0 = ix.size();
+          vm.resize(v0 + h.val_cnt, 1);            // kind 1 = zero
+          ix.resize(i0 + h.idx_cnt, (uint16_t)dummy);
+          for (int t = 0; t < T; ++t) ix[i0 + (size_t)Q * T + t] = 0;   // meta of unused lanes: not a head, nothing behind
+          for (int sgi = 0; sgi < nr; ++sgi) {
+            const Seg &sg = segs[sgi];
+            const int64_t r = sg.row;
+            const int cnt = count(r);
+            const int64_t kb = P.h_rowptr[r] + (dir == 0 ? 0 : P.h_diag[r] + 1);
+            for (int l = 0; l < sg.k; ++l) {
+              const int t = sg.lane0 + l;
+              for (int q = 0; q < Q; ++q) {
+                const int e2 = l * Q + q;
+                if (e2 >= cnt) break;
+                vm[v0 + (size_t)q * T + t] = (kb + e2) << 2;
+                ix[i0 + (size_t)q * T + t] = (uint16_t)(P.h_col[kb + e2] - r0);
               }
-          for (int s = 0; s < nrp; ++s) {
-            if (s < nr) {
-              const int64_t r = rows[at + s];
-              vm.push_back(((P.h_rowptr[r] + P.h_diag[r]) << 2) | (dir == 0 ? 2 : 3));
-              ix.push_back((uint16_t)(r - r0));
-            } else { vm.push_back(1); ix.push_back((uint16_t)dummy); }
+              ix[i0 + (size_t)Q * T + t] = (uint16_t)((l == 0 ? 0x8000 : 0) | (sgi << 5) | (sg.k - 1 - l));
+            }
+            vm[v0 + (size_t)Q * T + sgi] = ((P.h_rowptr[r] + P.h_diag[r]) << 2) | (dir == 0 ? 2 : 3);
+            ix[i0 + (size_t)Q * T + T + sgi] = (uint16_t)(r - r0);
           }
-          at += nr;
+          at = next;
         }
         a = e;
       }
     }
   }
   if (!err.empty()) throw std::runtime_error(err);
-  int64_t nval = 0, npass = 0;
-  int max_pass = 0, stage = 0;
+  int64_t nval = 0, nidx = 0, npass = 0;
+  int max_pass = 0;
   for (int b = 0; b < nb; ++b) {
-    blk[b].val_base = nval; blk[b].idx_base = nval;   // both streams hold one element per slot
+    blk[b].val_base = nval; blk[b].idx_base = nidx;
     blk[b].pass0 = (int)npass; blk[b].npass = (int)pass[b].size();
     blk[b].row0 = (int)P.blk_off[b]; blk[b].nrows = (int)(P.blk_off[b + 1] - P.blk_off[b]);
-    if (vmap[b].size() >= ((size_t)1 << 31)) throw std::runtime_error("block-local sweep: block stream exceeds 2^31 entries");
-    nval += (int64_t)vmap[b].size(); npass += blk[b].npass;
+    if (vmap[b].size() >= ((size_t)1 << 31) || idx[b].size() >= ((size_t)1 << 31)) throw std::runtime_error("block-local sweep: block stream exceeds 2^31 entries");
+    nval += (int64_t)vmap[b].size(); nidx += (int64_t)idx[b].size(); npass += blk[b].npass;
     max_pass = std::max(max_pass, blk[b].npass);
-    for (const int4 &h : pass[b]) stage = std::max(stage, ((h.z >> 16) & 0xffff) * (h.z & 0xffff) * (1 << (h.w & 0xff)) + (h.z & 0xffff));
+  }
+  // ring schedule: every pass gets a fixed region of the shared-memory ring and the number of the pass whose consumption
+  // frees it (passes are consumed in order), so the producer warp needs no bookkeeping
+  const size_t fixed = bl_fixed_smem(max_rows, max_pass);
+  if (fixed + 2 * (size_t)PASS_BYTES_MAX > 227 * 1024) throw std::runtime_error("block-local sweep: shared memory budget exceeded");
+  const int ring_bytes = (int)((227 * 1024 - fixed) / 128 * 128);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < nb; ++b) {
+    std::vector<PassHdr> &ps = pass[b];
+    std::vector<int> beg(ps.size()), end(ps.size());
+    int head = 0, oldest = 0;   // oldest: first pass still resident
+    for (int p = 0; p < (int)ps.size(); ++p) {
+      const int bytes = (ps[p].val_cnt * 8 + ps[p].idx_cnt * 2 + 127) / 128 * 128;
+      if (head + bytes > ring_bytes) head = 0;
+      int wait = p - NSLOT;   // the barrier pair of this slot must have been released
+      // evict every resident pass that overlaps [head, head + bytes)
+      while (oldest < p) {
+        bool overlap = false;
+        for (int q = oldest; q < p; ++q)
+          if (beg[q] < head + bytes && head < end[q]) { overlap = true; break; }
+        if (!overlap) break;
+        wait = std::max(wait, oldest);
+        ++oldest;
+      }
+      beg[p] = head; end[p] = head + bytes;
+      ps[p].ring16 = head / 16;
+      ps[p].wait = wait;
+      if (wait >= 0) oldest = std::max(oldest, wait + 1);
+      head += bytes;
+    }
   }
   std::vector<int64_t> all_map(nval);
-  std::vector<uint16_t> all_idx(nval);
-  std::vector<int4> all_pass(npass);
+  std::vector<uint16_t> all_idx(nidx);
+  std::vector<PassHdr> all_pass(npass);
 #pragma omp parallel for schedule(dynamic, 1)
   for (int b = 0; b < nb; ++b) {
     std::copy(vmap[b].begin(), vmap[b].end(), all_map.begin() + blk[b].val_base);
@@ -296,20 +374,19 @@ void bl_build(Ctx &c, TriPlan &P) {
     std::copy(pass[b].begin(), pass[b].end(), all_pass.begin() + blk[b].pass0);
   }
   P.bl_nval = nval;
-  P.bl_max_rows = max_rows; P.bl_max_pass = (max_pass + 3) / 4 * 4;
-  P.bl_stage_val = (stage + 15) / 16 * 16;   // 128-byte multiples for both sections
-  P.bl_stage_idx = (stage + 63) / 64 * 64;
+  P.bl_max_rows = max_rows; P.bl_max_pass = max_pass; P.bl_ring = ring_bytes;
   P.bl_map.upload(all_map, c.stream);
-  P.bl_idx.alloc_padded(nval, 64, c.stream);
-  NSX_CUDA(cudaMemcpyAsync(P.bl_idx.p, all_idx.data(), nval * sizeof(uint16_t), cudaMemcpyHostToDevice, c.stream));
+  P.bl_idx.alloc_padded(nidx, 64, c.stream);
+  NSX_CUDA(cudaMemcpyAsync(P.bl_idx.p, all_idx.data(), nidx * sizeof(uint16_t), cudaMemcpyHostToDevice, c.stream));
   P.bl_val.alloc_padded(nval, 16, c.stream);
-  P.bl_pass.upload(all_pass, c.stream);
+  P.bl_pass.alloc(npass * sizeof(PassHdr));
+  NSX_CUDA(cudaMemcpyAsync(P.bl_pass.p, all_pass.data(), npass * sizeof(PassHdr), cudaMemcpyHostToDevice, c.stream));
   P.bl_blk.upload(blk, c.stream);
   P.bl_sgs = -1;
   NSX_CUDA(cudaStreamSynchronize(c.stream));
   if (c.verbose) {
-    fprintf(stderr, "[nsx] block-local sweep plan: %d blocks, rows/block max %d, %lld passes (max %d per block), %lld stream slots for %lld non-zeros (%.1f%% padding), stage %d entries\n",
-            nb, max_rows, (long long)npass, max_pass, (long long)nval, (long long)P.nnz, 100.0 * (double)(nval - P.nnz) / (double)std::max<int64_t>(1, P.nnz), stage);
+    fprintf(stderr, "[nsx] block-local sweep plan: %d blocks, rows/block max %d, %lld passes (max %d per block), %.1f MB of values + %.1f MB of indices for %lld non-zeros (%.2f B per non-zero), ring %d KB\n",
+            nb, max_rows, (long long)npass, max_pass, nval * 8e-6, nidx * 2e-6, (long long)P.nnz, (nval * 8.0 + nidx * 2.0) / (double)std::max<int64_t>(1, P.nnz), ring_bytes / 1024);
   }
 }
 
@@ -323,9 +400,7 @@ void bl_refresh(Ctx &c, TriPlan &P, bool sgs) {
 void bl_sweep(Ctx &c, TriPlan &P, bool sgs, double *y, const double *x, const double *scale, double *v_out, const int *gate) {
   if (P.bl_sgs != (sgs ? 1 : 0)) throw std::logic_error("block-local sweep: the stream does not hold the values of this preconditioner");
   if (!P.nblk || !P.n) return;
-  const size_t smem = (size_t)NSTAGE * ((size_t)P.bl_stage_val * 8 + (size_t)P.bl_stage_idx * 2) + (size_t)(P.bl_max_rows + 8) * 8 +
-                      (size_t)P.bl_max_pass * 16 + NSTAGE * 8;
-  if (smem > 227 * 1024) throw std::runtime_error("block-local sweep: shared memory budget exceeded");
+  const size_t smem = (size_t)P.bl_ring + bl_fixed_smem(P.bl_max_rows, P.bl_max_pass);
   static std::map<std::pair<int, int>, size_t> attr;   // (device, kernel) -> limit already granted
   size_t &lim = attr[{c.device, sgs ? 1 : 0}];
   if (lim < smem) {
@@ -333,12 +408,11 @@ void bl_sweep(Ctx &c, TriPlan &P, bool sgs, double *y, const double *x, const do
     else NSX_CUDA(cudaFuncSetAttribute(k_sweep_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lim = smem;
   }
+  const PassHdr *ph = reinterpret_cast<const PassHdr *>(P.bl_pass.p);
   if (sgs)
-    k_sweep_block<true><<<P.nblk, NT, smem, c.stream>>>(P.bl_blk.p, P.bl_pass.p, P.bl_val.p, P.bl_idx.p, P.perm.p, x, y, scale, v_out, gate,
-                                                         P.bl_max_rows, P.bl_max_pass, P.bl_stage_val, P.bl_stage_idx);
+    k_sweep_block<true><<<P.nblk, NT, smem, c.stream>>>(P.bl_blk.p, ph, P.bl_val.p, P.bl_idx.p, P.perm.p, x, y, scale, v_out, gate, P.bl_max_rows, P.bl_max_pass, P.bl_ring);
   else
-    k_sweep_block<false><<<P.nblk, NT, smem, c.stream>>>(P.bl_blk.p, P.bl_pass.p, P.bl_val.p, P.bl_idx.p, P.perm.p, x, y, scale, v_out, gate,
-                                                          P.bl_max_rows, P.bl_max_pass, P.bl_stage_val, P.bl_stage_idx);
+    k_sweep_block<false><<<P.nblk, NT, smem, c.stream>>>(P.bl_blk.p, ph, P.bl_val.p, P.bl_idx.p, P.perm.p, x, y, scale, v_out, gate, P.bl_max_rows, P.bl_max_pass, P.bl_ring);
   c.stat_launches++;
 }
 

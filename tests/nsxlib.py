@@ -11,7 +11,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from navier_stokes_solver_b200.binding import *  # noqa: E402,F401,F403
-from navier_stokes_solver_b200.binding import Device, Disc, NsxError, nsx, ptr, synthetic_state  # noqa: E402,F401
+from navier_stokes_solver_b200.binding import Device, Disc, NsxError, nsx, nsx_host, ptr, synthetic_state  # noqa: E402,F401
 from oracle.pyoracle import Oracle, orc  # noqa: E402,F401
 
 

@@ -19,12 +19,17 @@ def declared(header):
 
 
 def test_every_declared_symbol_is_exported():
-    L = N.nsx()
-    names = declared("nsx.h") + declared("nsx_host.h")
-    assert len(names) > 40
-    missing = [n for n in names if not hasattr(L, n)]
+    L, H = N.nsx(), N.nsx_host()
+    names, host_names = declared("nsx.h"), declared("nsx_host.h")
+    assert len(names) > 40 and len(host_names) >= 8
+    missing = [n for n in names if not hasattr(L, n)] + [n for n in host_names if not hasattr(H, n)]
     assert not missing, missing
-    assert sorted(N.NSX_SYMBOLS) == declared("nsx.h")
+    assert sorted(N.NSX_SYMBOLS) == names
+    assert sorted(N.NSX_HOST_SYMBOLS) == host_names
+    # the host set-up stand-in is its own library: the CPU legs of bench.py and the oracle tests never map the CUDA library
+    import subprocess
+    out = subprocess.run(["ldd", N.LIBNSX_HOST], stdout=subprocess.PIPE, text=True).stdout
+    assert "libcudart" not in out and "libnsx.so" not in out
 
 
 def test_no_cpu_fallback():
