@@ -13,8 +13,13 @@ line-search re-assembly and its residual norm.  Every step restarts from the sam
   value : step time with all inputs resident in HBM (device-side reset of the state)
   e2e   : the same step through the C ABI with HOST buffers: the state is uploaded from pinned host
           memory and the new solution is read back inside the timed region
-  roofline : the Jacobian block SpMV kernel, algorithmic bytes / CUDA-event time, L2 flushed
-  cpu_baseline : the CPU oracle (port of the reference path) on the host cores, bounded sample
+  roofline : the kernel with the largest share of the step (the ILU / SGS sweep), algorithmic bytes / CUDA-event time
+  spmv_roofline : the Jacobian block SpMV the metric names
+  cpu_baseline : the CPU oracle (port of the reference path) on the host cores, bounded sample, extrapolated (says so)
+
+--budget-s (default 780): a safety net for the driver's wall-clock limit.  The first warm-up step is timed; when W + K steps
+plus the kernel timings and the CPU sample would not fit the budget, the step COUNT is lowered (never the work inside a
+step), the JSON line carries the counts actually run and config.budget_guard says what was asked for.
 """
 import argparse
 import json
@@ -95,29 +100,56 @@ def parse_mesh(s):
     return int(a), int(b)
 
 
-def cpu_step_sample(nx, ny, solver, prec, tol, nu, outer_cap, threads=None):
-    """Bounded sample of the step on the CPU oracle: both assemblies in full, the solve capped at `outer_cap` outer iterations.
+class CpuSampler:
+    """Bounded samples of the step on the CPU oracle: both assemblies in full, the solve capped at a number of outer iterations
+    (raised once so that the capped solve lasts about `target_s` seconds, when target_s > 0).
     The reference runs one MPI rank per core (mpirun -n N) and its Ifpack / ML inner preconditioners are rank-local, so the
     oracle gets the mesh partitioned into one rank-local block per host thread: its SGS / ILU sweeps then run in parallel
-    over the blocks exactly as the reference's ranks would.  Returns (t_assemble_each, t_solve_capped, outer_done, threads)."""
-    from navier_stokes_solver_b200 import binding as B
-    from oracle.pyoracle import Oracle, orc
-    if threads:
-        orc().orc_set_threads(threads)
-    threads = int(orc().orc_get_threads())
-    o = Oracle(B.Disc.generate(nx, ny, nranks=threads))
-    t0 = time.perf_counter()
-    o.assemble(0, True, nu)
-    t_asm = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    rc, it, fr, inner = o.solve(0, solver, prec, tol, outer_cap)
-    t_solve = time.perf_counter() - t0
-    return t_asm, t_solve, max(it, 1), threads
+    over the blocks exactly as the reference's ranks would."""
+
+    def __init__(self, nx, ny, solver, prec, tol, nu, threads=None):
+        from navier_stokes_solver_b200 import binding as B
+        from oracle.pyoracle import Oracle, orc
+        if threads:
+            orc().orc_set_threads(threads)
+        self.threads = int(orc().orc_get_threads())
+        self.o = Oracle(B.Disc.generate(nx, ny, nranks=self.threads))
+        self.solver, self.prec, self.tol, self.nu = solver, prec, tol, nu
+        self.cap = None
+
+    def _capped(self, cap):
+        o = self.o
+        o.vec(0)[:] = 0
+        o.vec(2)[:] = 0
+        t0 = time.perf_counter()
+        o.assemble(0, True, self.nu)
+        t_asm = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        rc, it, fr, inner = o.solve(0, self.solver, self.prec, self.tol, cap)
+        return {"t_asm": t_asm, "t_solve": time.perf_counter() - t0, "outer_done": max(it, 1), "converged": rc == 0,
+                "threads": self.threads, "inner_F": int(inner[0]), "inner_S": int(inner[1])}
+
+    def sample(self, outer_cap, target_s=0.0):
+        if self.cap is None:   # calibrate once: how many outer iterations last about target_s
+            r = self._capped(outer_cap)
+            self.cap = outer_cap
+            if target_s > 0 and not r["converged"] and r["t_solve"] < 0.5 * target_s:
+                self.cap = int(min(400, max(outer_cap + 1, outer_cap * target_s / max(r["t_solve"], 1e-3))))
+                r = self._capped(self.cap)
+            return r
+        return self._capped(self.cap)
 
 
-# outer FGMRES iterations of the full solve, measured on the B200 (profiles/r01_bench_1gpu_300x100.json): the CPU sample runs a few outer
-# iterations and is scaled linearly to this count (early iterations are the cheap ones, so the scaling favours the CPU)
-MEASURED_OUTER = {("300,100", 1, 0): 817}
+def outer_total_fixture(mesh, solver, prec):
+    """Outer iteration count of the FULL first-step solve by the CPU oracle itself (profiles/oracle_full_solves.json, written by
+    tools/oracle_full_solve.py in the build container: the solve takes about an hour of 8 cores, far beyond a bench lease)."""
+    p = os.path.join(ROOT, "profiles", "oracle_full_solves.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            for rec in json.load(f):
+                if rec["mesh"] == mesh and rec["solver"] == solver and rec["prec"] == prec:
+                    return rec
+    return None
 
 
 def workload_name(args, nx, ny):
@@ -126,11 +158,15 @@ def workload_name(args, nx, ny):
 
 
 def run_reference(args, emit):
-    """--impl reference: the reference's CPU implementation of the path.  deal.II / Trilinos / MPI are
-    not installable in this image, so the timed code is the oracle port of the reference path
-    (oracle/, OpenMP over the host cores).  Each step is a bounded sample: both assemblies in full plus
-    the solve capped at --cpu-outer-cap outer iterations, scaled linearly in outer iterations to the count
-    the full solve needs (--cpu-outer-total, default: the count measured on the GPU for this configuration)."""
+    """--impl reference: the reference's CPU implementation of the path.  deal.II / Trilinos / MPI are not installable in this
+    image, so the timed code is the oracle port of the reference path (oracle/, OpenMP over all host cores, one rank-local
+    preconditioner block per thread as under mpirun).  A whole step of the 300x100 configuration takes the CPU the better
+    part of an hour, so each bench step is a BOUNDED SAMPLE: both assemblies in full plus the solve capped at a number of outer
+    iterations that lasts about --cpu-sample-s seconds; `value` is that sample extrapolated linearly in outer iterations to
+    the count of the full solve (early outer iterations are the cheap ones -- their inner solves converge fastest -- so the
+    scaling favours the CPU).  The line says `extrapolated`, and carries the measured seconds beside the extrapolated ones.
+    The full count comes from the oracle's own complete solve (profiles/oracle_full_solves.json) or --cpu-outer-total; meshes
+    small enough are simply solved in full (no extrapolation)."""
     from navier_stokes_solver_b200 import binding as B
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -138,22 +174,34 @@ def run_reference(args, emit):
     nx, ny = parse_mesh(args.mesh)
     d = B.Disc.generate(nx, ny)
     nu = 1.0 / 10.0
-    times = []
-    cores = 1
-    total = args.cpu_outer_total or MEASURED_OUTER.get((args.mesh, args.solver, args.prec), 0)
+    fixture = outer_total_fixture(args.mesh, args.solver, args.prec)
+    total = args.cpu_outer_total or (fixture["outer"] if fixture else 0)
+    small = d.n < 40000   # solved in full
+    times, meas = [], []
+    smp = None
+    sampler = CpuSampler(nx, ny, args.solver, args.prec, args.tol, nu)
     for s in range(args.warmup + args.steps):
-        t_asm, t_solve, it, cores = cpu_step_sample(nx, ny, args.solver, args.prec, args.tol, nu, args.cpu_outer_cap)
-        t = 2 * t_asm + t_solve * ((total or it) / it)
+        smp = sampler.sample(20000 if small else args.cpu_outer_cap, target_s=0.0 if small else 0.5 * args.cpu_sample_s)
+        full = smp["converged"]
+        scale = 1.0 if full else max(1.0, (total or smp["outer_done"]) / smp["outer_done"])
         if s >= args.warmup:
-            times.append(t)
+            times.append(2 * smp["t_asm"] + smp["t_solve"] * scale)
+            meas.append(2 * smp["t_asm"] + smp["t_solve"])
     val = float(np.mean(times))
-    sample = (f"oracle port, mesh cut into {cores} rank-local blocks on {cores} host threads (as mpirun -n {cores}): 2 full assemblies ({t_asm:.2f} s each) + solve capped at {it} outer iterations "
-              f"({t_solve:.2f} s), scaled linearly to {total or it} outer iterations")
+    extrapolated = not smp["converged"]
+    cores = smp["threads"]
+    sample = (f"oracle port, mesh cut into {cores} rank-local blocks on {cores} host threads (as mpirun -n {cores}): 2 full assemblies "
+              f"({smp['t_asm']:.2f} s each) + solve " +
+              (f"run to convergence ({smp['outer_done']} outer iterations, {smp['t_solve']:.2f} s)" if not extrapolated else
+               f"capped at {smp['outer_done']} outer iterations ({smp['t_solve']:.2f} s measured), extrapolated linearly to {total or smp['outer_done']} outer iterations "
+               f"({'the count of the oracle`s own full solve, profiles/oracle_full_solves.json' if fixture and not args.cpu_outer_total else '--cpu-outer-total' if args.cpu_outer_total else 'no full count known: NOT extrapolated'})"))
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": val * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "impl": "reference",
+            "data": "synthetic", "impl": "reference", "extrapolated": extrapolated,
+            "measured_sample_s": float(np.mean(meas)),
             "config": {"workload": workload_name(args, nx, ny), "cells": d.ncells, "dofs": d.n},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "extrapolated": extrapolated,
+                             "measured_s": float(np.mean(meas)), "outer_done": smp["outer_done"], "outer_total": total or smp["outer_done"]},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -276,14 +324,17 @@ def main():
     ap.add_argument("--solver", type=int, default=1)
     ap.add_argument("--prec", type=int, default=0)
     ap.add_argument("--tol", type=float, default=1e-10)
-    ap.add_argument("--ordering", type=int, default=1, help="ILU/SGS elimination order: 0 natural (as Ifpack), 1 multicolour")
+    ap.add_argument("--ordering", type=int, default=2, help="ILU/SGS elimination order: 0 natural (as Ifpack), 1 multicolour over the owned range, 2 multicolour inside CTA-local blocks (library default)")
+    ap.add_argument("--budget-s", type=float, default=780.0, help="wall-clock budget of the whole run; the step count shrinks to fit (0: off)")
+    ap.add_argument("--cpu-sample-s", type=float, default=15.0, help="length of the capped CPU solve of the cpu_baseline / reference arm")
     ap.add_argument("--unsteady-mesh", default="gmsh", help="unsteady workload: 'gmsh' = the reference's new_mesh.msh (P2/P1), X,Y = generated Q3/Q2 mesh, tri:X,Y = generated P2/P1 mesh")
     ap.add_argument("--ortho", type=int, default=None, help="Gram-Schmidt variant (NSX_OPT_ORTHO); default: the library's")
-    ap.add_argument("--cpu-outer-cap", type=int, default=1)
+    ap.add_argument("--cpu-outer-cap", type=int, default=2)
     ap.add_argument("--cpu-outer-total", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--kernel-reps", type=int, default=50)
     args = ap.parse_args()
+    t_process = time.perf_counter()
     # stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL's version banner, library chatter)
     # is routed to stderr for the duration of the run
     real_stdout = os.dup(1)
@@ -378,21 +429,47 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.SUM)
         return float(tt.item())
 
-    for _ in range(args.warmup):
+    # budget guard: time the first warm-up step, then fit W + K steps, the kernel timings and the CPU sample into --budget-s by
+    # lowering the step COUNT (never the work inside a step); the line reports the counts actually run
+    warmup, steps = args.warmup, args.steps
+    guard = None
+    if warmup + steps > 0:
+        barrier()
+        t1 = time.perf_counter()
         step()
+        barrier()
+        t1 = max_over_ranks(time.perf_counter() - t1)
+        done = 1
+        if args.budget_s > 0:
+            reserve = 40.0 + (0.0 if (args.no_cpu or world > 1) else 2.5 * args.cpu_sample_s + 10.0)
+            left = args.budget_s - max_over_ranks(time.perf_counter() - t_process) - reserve
+            afford = int(left / max(t1, 1e-3))   # further steps that fit
+            want = max(0, warmup - 1) + steps
+            if afford < want:
+                w2 = min(warmup, 3)
+                k2 = max(1, afford - max(0, w2 - 1))
+                if afford < max(0, w2 - 1) + 1:
+                    w2, k2 = max(1, min(w2, afford)), 1
+                guard = {"budget_s": args.budget_s, "requested_steps": steps, "requested_warmup": warmup, "first_step_s": t1,
+                         "note": "step count lowered to fit the wall-clock budget; every step still does the full work"}
+                warmup, steps = w2, k2
+        for _ in range(max(0, warmup - done)):
+            step()
+        if warmup == 0:
+            warmup = 1   # the timed first step was a warm-up in effect
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     # timed region: K steps between barriers, CUDA events on the library's stream; the host<->device copies are
     # bracketed by their own events so that the device-resident time (value) is the same steps minus the copies
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     l0 = dev.stat("KERNEL_LAUNCHES")
     spmv0 = dev.stat("SPMV_CALLS")
     t_wall = time.perf_counter()
     e_begin.record(stream)
-    for k in range(args.steps):
+    for k in range(steps):
         step(evs[k])
     e_end.record(stream)
     barrier()
@@ -401,9 +478,9 @@ def main():
     spmv_calls = dev.stat("SPMV_CALLS") - spmv0
     total_ms = e_begin.elapsed_time(e_end)
     copy_ms = sum(e[0].elapsed_time(e[1]) + e[2].elapsed_time(e[3]) for e in evs)
-    e2e_s = max_over_ranks(total_ms) / 1e3 / args.steps
-    value = max_over_ranks(total_ms - copy_ms) / 1e3 / args.steps
-    wall_s = max_over_ranks(t_wall) / args.steps
+    e2e_s = max_over_ranks(total_ms) / 1e3 / steps
+    value = max_over_ranks(total_ms - copy_ms) / 1e3 / steps
+    wall_s = max_over_ranks(t_wall) / steps
     launches_all = int(sum_over_ranks(float(launches)))
     h2d = int(sum_over_ranks(16.0 * n))
     d2h = int(sum_over_ranks(8.0 * n + 16))
@@ -436,6 +513,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     nnz = {b: dev.nnz(b) for b in (B.BLOCK_F, B.BLOCK_BT, B.BLOCK_B, B.BLOCK_MP)}
+    sb = dev.sweep_blocks(B.BLOCK_F)
+    sweep_blocks = len(sb[0]) - 1 if sb else 0
     nnz_j = nnz[B.BLOCK_F] + nnz[B.BLOCK_BT] + nnz[B.BLOCK_B]
     peak, peak_kind = load_peaks()
     n_u_own, ncells_own = dev.n_u, d.ncells
@@ -472,17 +551,25 @@ def main():
         kernels[k]["ms_back_to_back"] = k_b2b[k]
     # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture of
     # this configuration on one B200 (profiles/r01_prof_r1_top_kernels.md); null for any other mesh / partition
-    ncu_traffic = {"sgs_F": 478.5e6 + 11.9e6, "block_spmv": 448.1e6 + 9.2e6, "spmv_F": 278.4e6 + 7.9e6} if (args.mesh == "300,100" and world == 1) else {}
+    ncu_traffic = {}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # written from an `ncu --set full` capture by tools/ncu_summary.py --traffic
+    if os.path.exists(tp) and world == 1:
+        with open(tp) as f:
+            rec = json.load(f)
+        if rec.get("mesh") == args.mesh and rec.get("ordering") == args.ordering:
+            ncu_traffic = rec.get("bytes_per_launch", {})
     dom = max(share, key=share.get)
-    dom_kernel = {"sgs_F": "k_sweep_phased<SGS> (symmetric Gauss-Seidel sweeps on F, inner preconditioner of the inner FGMRES)",
+    sweep_kernel = {0: "k_tri_level / k_tri_chain", 1: "k_sweep_phased<SGS>", 2: "k_sweep_block<SGS>"}[args.ordering]
+    dom_kernel = {"sgs_F": sweep_kernel + " (symmetric Gauss-Seidel sweeps on F, inner preconditioner of the inner FGMRES)",
                   "spmv_F": "k_spmv_tma (F SpMV of the inner FGMRES)", "block_spmv": "k_spmv_tma (Jacobian block SpMV)"}[dom]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": workload_name(args, nx, ny), "cells": g.ncells, "dofs": g.n, "nnz_J_rank0": nnz_j,
                    "partition": f"{world} strips of cells, owned rows per rank (rank 0: {n} dofs)" if world > 1 else "one rank",
-                   "elimination_order": "multicolour" if args.ordering else "natural", "ortho_option": args.ortho,
+                   "elimination_order": ["natural (Ifpack)", "multicolour over the owned range", f"multicolour inside {sweep_blocks} CTA-local blocks (Ifpack overlap 0 at one rank per block)"][args.ordering],
+                   "ortho_option": args.ortho, "budget_guard": guard,
                    "outer_iterations": stats["outer"], "inner_F_iterations": stats["inner_F"], "inner_Mp_or_S_iterations": stats["inner_S"],
                    "final_residual": stats["final_res"],
                    "l2_policy": "step: working set (0.5 GB matrix + 60 Krylov vectors) exceeds the 126 MB L2; kernel timings: SpMV / sweep inputs (330-510 MB) exceed L2 and are timed back to back in one event pair (the L2-flushed single-launch times are listed beside them), vector kernels flush L2 (512 MiB) before every launch",
@@ -499,11 +586,19 @@ def main():
         "kernels": kernels,
     }
     if rank == 0 and not args.no_cpu and world == 1:
-        t_asm, t_solve, it, cores = cpu_step_sample(nx, ny, args.solver, args.prec, args.tol, nu, args.cpu_outer_cap)
-        cpu_val = 2 * t_asm + t_solve * (stats["outer"] / it)
-        line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"oracle port, mesh cut into {cores} rank-local blocks on {cores} host threads (as mpirun -n {cores}): 2 full assemblies ({t_asm:.2f} s each) + solve capped at {it} outer "
-                                          f"iterations ({t_solve:.2f} s), scaled to the GPU run's {stats['outer']} outer iterations"}
+        smp = CpuSampler(nx, ny, args.solver, args.prec, args.tol, nu).sample(args.cpu_outer_cap, target_s=args.cpu_sample_s)
+        fixture = outer_total_fixture(args.mesh, args.solver, args.prec)
+        total = args.cpu_outer_total or (fixture["outer"] if fixture else stats["outer"])
+        src = "--cpu-outer-total" if args.cpu_outer_total else ("the oracle's own full solve (profiles/oracle_full_solves.json)" if fixture else "this run's GPU solve")
+        extrapolated = not smp["converged"]
+        scale = max(1.0, total / smp["outer_done"]) if extrapolated else 1.0
+        cpu_val = 2 * smp["t_asm"] + smp["t_solve"] * scale
+        cores = smp["threads"]
+        line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "extrapolated": extrapolated,
+                                "measured_s": 2 * smp["t_asm"] + smp["t_solve"], "outer_done": smp["outer_done"], "outer_total": total if extrapolated else smp["outer_done"],
+                                "sample": f"oracle port, mesh cut into {cores} rank-local blocks on {cores} host threads (as mpirun -n {cores}): 2 full assemblies ({smp['t_asm']:.2f} s each) + solve " +
+                                          (f"capped at {smp['outer_done']} outer iterations ({smp['t_solve']:.2f} s measured), extrapolated linearly to {total} outer iterations, the count of {src}"
+                                           if extrapolated else f"run to convergence ({smp['outer_done']} outer iterations, {smp['t_solve']:.2f} s)")}
     if rank == 0:
         emit(line)
     dev.close()

@@ -16,8 +16,8 @@
 //              neighbour (ML phase 2).  Aggregates never cross an owned-range boundary (uncoupled).
 //   P          (I - 4/3 / lambda_max D^-1 A) P_tent, P_tent(i, agg(i)) = 1;  R = P^T;  A_c = R A P
 //   lambda_max of D^-1 A from 10 CG-Lanczos steps (ML "eigen-analysis: type" cg)
-//   smoother   Chebyshev polynomial of degree 2 in D^-1 A on [lambda_max / 20, 1.1 lambda_max]
-//   coarsest   <= 128 rows (or level 10): dense inverse by Gauss-Jordan with partial pivoting
+//   smoother   Chebyshev polynomial of degree 2 in D^-1 A on [lambda_max / 10, 1.1 lambda_max]
+//   coarsest   <= 2000 rows (or level 10; deal.II sets "coarse: max size" = 2000 and "smoother: Chebyshev alpha" = 10 on top of ML's SA defaults): dense inverse by Gauss-Jordan with partial pivoting
 // The sparse products are expand - sort - compress: every scalar product a_ik b_kj is written out with the key
 // (i, j), a stable radix sort groups equal keys, and one thread per distinct key adds its run in sorted order
 // (deterministic).  Level operators are plain CSR and go through the library's own SpMV kernels.
@@ -31,8 +31,8 @@ namespace nsx {
 
 namespace {
 
-constexpr double AMG_THRESHOLD = 1e-4, AMG_EIG_RATIO = 20.0, AMG_EIG_BOOST = 1.1;
-constexpr int AMG_MAX_LEVELS = 10, AMG_COARSE_MAX = 128, AMG_CHEBY_DEGREE = 2, AMG_DENSE_MAX = 4096;
+constexpr double AMG_THRESHOLD = 1e-4, AMG_EIG_RATIO = 10.0, AMG_EIG_BOOST = 1.1;
+constexpr int AMG_MAX_LEVELS = 10, AMG_COARSE_MAX = 2000, AMG_CHEBY_DEGREE = 2, AMG_DENSE_MAX = 4096;
 
 __host__ __device__ inline uint32_t amg_hash(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;

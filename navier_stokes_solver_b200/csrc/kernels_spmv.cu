@@ -457,12 +457,12 @@ inline const int32_t *pairs_for(Ctx &c, const DevCSR &A_, const double *x) {
   return (A.pair_state == 1 && ((uintptr_t)x & 15) == 0) ? A.pcol.p : nullptr;
 }
 
-void tma_attr_once() {
-  static bool done = false;
-  if (done) return;
+void tma_attr_once(const Ctx &c) {   // cudaFuncSetAttribute applies per device
+  static std::vector<int> done;
+  if (std::find(done.begin(), done.end(), c.device) != done.end()) return;
   NSX_CUDA(cudaFuncSetAttribute(k_spmv_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
   NSX_CUDA(cudaFuncSetAttribute(k_spmv_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
-  done = true;
+  done.push_back(c.device);
 }
 
 inline int pick_group(const DevCSR &A) {
@@ -475,8 +475,9 @@ inline int pick_group(const DevCSR &A) {
 }  // namespace
 
 void spmv(Ctx &c, const DevCSR &A_, const double *x, double *y, bool add) {
+  // ghost import of the input first (no-op on one GPU): a rank that owns no row of this block still has to post its sends
+  halo_exchange(c, (&A_ == &c.F || &A_ == &c.B) ? 0 : 1, x);
   if (!A_.nrows) return;
-  halo_exchange(c, (&A_ == &c.F || &A_ == &c.B) ? 0 : 1, x);  // ghost import of the input (no-op on one GPU)
   spmv_local(c, A_, x, y, add);
 }
 
@@ -484,7 +485,7 @@ void spmv_local(Ctx &c, const DevCSR &A_, const double *x, double *y, bool add) 
   DevCSR &A = const_cast<DevCSR &>(A_);
   if (!A.nrows) return;
   if (c.stream_spmv >= 2 && !A.h_rowptr.empty() && A.nrows < (int64_t)1 << 31) {
-    tma_attr_once();
+    tma_attr_once(c);
     if (!A.ndesc) {
       std::vector<RowBlockDesc> h;
       append_row_descs(h, A, nullptr, 0);
@@ -518,7 +519,7 @@ void block_spmv(Ctx &c, const double *x, double *y) {
   halo_exchange(c, 0, x);
   halo_exchange(c, 1, x + c.n_u);
   if (c.stream_spmv >= 2 && n < (int64_t)1 << 31) {
-    tma_attr_once();
+    tma_attr_once(c);
     if (!c.ndesc_u) {
       std::vector<RowBlockDesc> h;
       append_row_descs(h, c.F, &c.Bt, 0);

@@ -34,8 +34,10 @@ namespace {
 constexpr int NC = 512;           // consumer threads (16 warps); one more warp feeds the ring
 constexpr int NT = NC + 32;
 constexpr int NSLOT = 16;         // passes in flight at most (full / empty barrier pairs)
-constexpr int MAX_BLOCK_ROWS = 8192;
-constexpr int PASS_BYTES_MAX = 40 * 1024;
+constexpr int BLOCKS_PER_SM = 2;   // CTAs resident per SM (shared memory is split between them)
+constexpr int MAX_BLOCK_ROWS = 4096;
+constexpr int PASS_BYTES_MAX = 32 * 1024;
+constexpr size_t SMEM_PER_CTA = (size_t)(227 * 1024 / BLOCKS_PER_SM - 1024) / 128 * 128;
 
 // Pass format ("lane-split rows"): a row with c entries in this sweep's triangle owns k = max(1, ceil(c / Q)) consecutive
 // lanes of one warp, Q entries each; rows are packed into warps first-fit.  With T = 32 x warps lanes in the pass:
@@ -47,7 +49,7 @@ constexpr int PASS_BYTES_MAX = 40 * 1024;
 struct PassHdr { int val_off, idx_off, ring16, wait; int tq, rrf, val_cnt, idx_cnt; };
 
 template <bool SGS>
-__global__ void __launch_bounds__(NT, 1) k_sweep_block(const BlkDesc *__restrict__ blks, const PassHdr *__restrict__ passes, const double *__restrict__ bl_val,
+__global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_sweep_block(const BlkDesc *__restrict__ blks, const PassHdr *__restrict__ passes, const double *__restrict__ bl_val,
                                                         const uint16_t *__restrict__ bl_idx, const int32_t *__restrict__ perm, const double *__restrict__ x,
                                                         double *__restrict__ y, const double *__restrict__ scale, double *__restrict__ v_out,
                                                         const int *__restrict__ gate, int max_rows, int max_pass, int ring_bytes) {
@@ -213,9 +215,10 @@ int geometric_blocks(Ctx &c, int block, const DevCSR &A, int64_t lo, int64_t hi,
   int64_t parts;
   if (c.block_rows > 0) parts = (n + c.block_rows - 1) / c.block_rows;
   else {
-    const int64_t per = n / std::max(1, c.num_sms);
-    if (per <= 512) parts = std::min<int64_t>(c.num_sms, (n + 256) / 512);
-    else parts = (int64_t)c.num_sms * ((per + 4095) / 4096);
+    // BLOCKS_PER_SM co-resident CTAs per SM hide each other's level latency; blocks of 512 .. 2048 rows, whole waves above
+    const int64_t slots = (int64_t)std::max(1, c.num_sms) * BLOCKS_PER_SM, per = n / slots;
+    if (per <= 512) parts = std::min<int64_t>(slots, (n + 256) / 512);
+    else parts = slots * ((per + 2047) / 2048);
   }
   parts = std::max<int64_t>(1, parts);
   rcb(pts, 0, n, (int)parts, first_group, grp);
@@ -248,6 +251,8 @@ void bl_build(Ctx &c, TriPlan &P) {
     struct Seg { int64_t row; int lane0, k; };
     std::vector<Seg> segs;
     std::vector<int> room;   // free lanes per warp of the pass under construction
+    std::vector<uint16_t> bank_used;
+    std::vector<int> left;
     for (int dir = 0; dir < 2; ++dir) {
       // levels ascending for the lower sweep, descending for the upper one; the rows of a level are contiguous
       int64_t a = dir == 0 ? r0 : r1;
@@ -299,16 +304,27 @@ void bl_build(Ctx &c, TriPlan &P) {
           vm.resize(v0 + h.val_cnt, 1);            // kind 1 = zero
           ix.resize(i0 + h.idx_cnt, (uint16_t)dummy);
           for (int t = 0; t < T; ++t) ix[i0 + (size_t)Q * T + t] = 0;   // meta of unused lanes: not a head, nothing behind
+          // Entries of a row may sit in any of its lanes' slots: place them so that the lanes of a half-warp gather from
+          // distinct 8-byte banks of the work vector where possible (a 64-bit shared-memory load is served per half-warp,
+          // 16 banks of 8 bytes)
+          bank_used.assign((size_t)(T / 16) * Q, 0);
           for (int sgi = 0; sgi < nr; ++sgi) {
             const Seg &sg = segs[sgi];
             const int64_t r = sg.row;
             const int cnt = count(r);
             const int64_t kb = P.h_rowptr[r] + (dir == 0 ? 0 : P.h_diag[r] + 1);
+            left.resize(cnt);
+            std::iota(left.begin(), left.end(), 0);
             for (int l = 0; l < sg.k; ++l) {
               const int t = sg.lane0 + l;
-              for (int q = 0; q < Q; ++q) {
-                const int e2 = l * Q + q;
-                if (e2 >= cnt) break;
+              for (int q = 0; q < Q && !left.empty(); ++q) {
+                uint16_t &used = bank_used[(size_t)(t / 16) * Q + q];
+                size_t pick = 0;
+                for (size_t u = 0; u < left.size(); ++u)
+                  if (!(used >> ((P.h_col[kb + left[u]] - r0) & 15) & 1)) { pick = u; break; }
+                const int e2 = left[pick];
+                left.erase(left.begin() + pick);
+                used |= (uint16_t)(1u << ((P.h_col[kb + e2] - r0) & 15));
                 vm[v0 + (size_t)q * T + t] = (kb + e2) << 2;
                 ix[i0 + (size_t)q * T + t] = (uint16_t)(P.h_col[kb + e2] - r0);
               }
@@ -337,8 +353,8 @@ void bl_build(Ctx &c, TriPlan &P) {
   // ring schedule: every pass gets a fixed region of the shared-memory ring and the number of the pass whose consumption
   // frees it (passes are consumed in order), so the producer warp needs no bookkeeping
   const size_t fixed = bl_fixed_smem(max_rows, max_pass);
-  if (fixed + 2 * (size_t)PASS_BYTES_MAX > 227 * 1024) throw std::runtime_error("block-local sweep: shared memory budget exceeded");
-  const int ring_bytes = (int)((227 * 1024 - fixed) / 128 * 128);
+  if (fixed + 2 * (size_t)PASS_BYTES_MAX > SMEM_PER_CTA) throw std::runtime_error("block-local sweep: shared memory budget exceeded");
+  const int ring_bytes = (int)((SMEM_PER_CTA - fixed) / 128 * 128);
 #pragma omp parallel for schedule(dynamic, 1)
   for (int b = 0; b < nb; ++b) {
     std::vector<PassHdr> &ps = pass[b];

@@ -660,10 +660,10 @@ static void sweep(Ctx &c, TriPlan &P, double *y, const double *x) {
                      : threads == 768 ? (const void *)k_sweep_phased<SGS, 768> : (const void *)k_sweep_phased<SGS, 512>;
     const int nthreads = (threads == 256 || threads == 384 || threads == 768) ? threads : 512;
     const size_t smem = (size_t)FCAP * nthreads * (sizeof(double) + sizeof(int32_t));
-    static std::vector<const void *> attr_done;  // kernels whose dynamic shared memory limit has been raised
-    if (std::find(attr_done.begin(), attr_done.end(), fn) == attr_done.end()) {
+    static std::vector<std::pair<int, const void *>> attr_done;  // (device, kernel) pairs whose dynamic shared memory limit has been raised
+    if (std::find(attr_done.begin(), attr_done.end(), std::make_pair(c.device, fn)) == attr_done.end()) {
       NSX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_done.push_back(fn);
+      attr_done.emplace_back(c.device, fn);
     }
     NSX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(c.num_sms), dim3(nthreads), args, smem, c.stream));
     P.barrier_epoch += (unsigned long long)(2 * ncol - 1) * (unsigned long long)c.num_sms;
