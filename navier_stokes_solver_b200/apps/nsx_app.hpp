@@ -5,7 +5,13 @@
 // In the reference this is NSSolverStationary::setup() / NSSolver::setup() (lab_new/src/NSSolverStationary.cpp:
 // 3-315, NSSolver.cpp:3-311) on top of deal.II; the hand-over below is the adapter INTEGRATION.md describes.
 #pragma once
+#include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
+
+#include <cctype>
+#include <cerrno>
+#include <ctime>
 
 #include <cstdint>
 #include <cstdio>
@@ -57,20 +63,50 @@ inline void check(nsx_ctx *ctx, int rc, const char *what) {
   throw std::runtime_error(msg + " (nsx status " + std::to_string(rc) + ")");
 }
 
-// NCCL id hand-over between the processes of one job: rank 0 writes the 128 bytes to a file, the others wait for it
-inline void exchange_comm_id(const Ranks &r, unsigned char id[128]) {
-  const char *dir = std::getenv("NSX_ID_DIR");
-  const char *port = std::getenv("MASTER_PORT");
-  const std::string path = std::string(dir ? dir : "/tmp") + "/nsx_comm_id_" + (port ? port : "0") + "_" + std::to_string((long)getppid());
+// NCCL id hand-over between the processes of one job: rank 0 writes the 128 bytes to a file, the others wait for it.
+// The name carries a job-unique token when the launcher provides one (torchrun's run id, the SLURM job + step, Open MPI's
+// job id, or NSX_JOB_ID), else the rendezvous port and the parent pid.  Rank 0 removes a leftover of the same name first,
+// creates the file exclusively (no symlink following) and removes it again once nsx_comm_init has returned (the NCCL
+// bootstrap is collective: every rank has read the id by then); the other ranks ignore files older than their own start.
+// The directory (NSX_ID_DIR, default /tmp) must be visible to every rank: a launch that spans nodes has to set it.
+inline std::string comm_id_path(const Ranks &r) {
+  auto env = [](const char *n) -> std::string { const char *v = std::getenv(n); return v ? v : ""; };
+  const std::string dir = env("NSX_ID_DIR");
+  long nodes = 1;
+  if (!env("SLURM_NNODES").empty()) nodes = std::atol(env("SLURM_NNODES").c_str());
+  else if (!env("OMPI_MCA_orte_num_nodes").empty()) nodes = std::atol(env("OMPI_MCA_orte_num_nodes").c_str());
+  else if (!env("LOCAL_WORLD_SIZE").empty() && std::atol(env("LOCAL_WORLD_SIZE").c_str()) > 0)
+    nodes = (r.size + std::atol(env("LOCAL_WORLD_SIZE").c_str()) - 1) / std::atol(env("LOCAL_WORLD_SIZE").c_str());
+  if (nodes > 1 && dir.empty())
+    throw std::runtime_error("this launch spans " + std::to_string(nodes) + " nodes: set NSX_ID_DIR to a directory every node can see (the NCCL id is handed over through a file)");
+  std::string token = env("NSX_JOB_ID");
+  if (token.empty()) token = env("TORCHELASTIC_RUN_ID");
+  if (token.empty() && !env("SLURM_JOB_ID").empty()) token = "slurm" + env("SLURM_JOB_ID") + "." + env("SLURM_STEP_ID");
+  if (token.empty()) token = env("OMPI_MCA_ess_base_jobid");
+  if (token.empty() || token == "none") token = "p" + env("MASTER_PORT") + "_" + std::to_string((long)getppid());
+  for (char &ch : token) if (!(std::isalnum((unsigned char)ch) || ch == '.' || ch == '_' || ch == '-')) ch = '_';
+  return (dir.empty() ? std::string("/tmp") : dir) + "/nsx_comm_id_" + std::to_string((long)getuid()) + "_" + token;
+}
+
+inline void exchange_comm_id(const Ranks &r, unsigned char id[128], const std::string &path) {
+  const time_t started = time(nullptr);
   if (r.rank == 0) {
     if (nsx_comm_unique_id(id) != NSX_OK) throw std::runtime_error("nsx_comm_unique_id failed (NCCL not loadable?)");
     const std::string tmp = path + ".tmp";
-    { std::ofstream f(tmp, std::ios::binary); f.write((const char *)id, 128); }
-    std::rename(tmp.c_str(), path.c_str());
+    unlink(path.c_str());
+    unlink(tmp.c_str());
+    const int fd = open(tmp.c_str(), O_CREAT | O_EXCL | O_WRONLY | O_NOFOLLOW, 0600);
+    if (fd < 0) throw std::runtime_error("cannot create the NCCL id file " + tmp + ": " + std::strerror(errno));
+    const ssize_t w = write(fd, id, 128);
+    close(fd);
+    if (w != 128 || std::rename(tmp.c_str(), path.c_str()) != 0) { unlink(tmp.c_str()); throw std::runtime_error("cannot write the NCCL id file " + path); }
   } else {
     for (int tries = 0;; ++tries) {
-      std::ifstream f(path, std::ios::binary);
-      if (f && f.read((char *)id, 128)) break;
+      struct stat st;
+      if (lstat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode) && st.st_uid == getuid() && st.st_size == 128 && st.st_mtime >= started - 120) {
+        std::ifstream f(path, std::ios::binary);
+        if (f && f.read((char *)id, 128)) break;
+      }
       if (tries > 6000) throw std::runtime_error("timed out waiting for the NCCL id file " + path);
       usleep(10000);
     }
@@ -141,8 +177,11 @@ struct Problem {
     check(ctx, nsx_set_dirichlet(ctx, nbc, bc, inlet.data()), "nsx_set_dirichlet");
     if (local) {
       unsigned char id[128];
-      exchange_comm_id(ranks, id);
-      check(ctx, nsx_comm_init(ctx, id), "nsx_comm_init");
+      const std::string id_path = comm_id_path(ranks);
+      exchange_comm_id(ranks, id, id_path);
+      const int rc_comm = nsx_comm_init(ctx, id);
+      if (ranks.rank == 0) unlink(id_path.c_str());   // every rank has joined (or the bootstrap failed): the file has served
+      check(ctx, rc_comm, "nsx_comm_init");
     } else {
       check(ctx, nsx_set_ranks(ctx, 1, arr<int64_t>(NSX_DA_OWNED_U), arr<int64_t>(NSX_DA_OWNED_P)), "nsx_set_ranks");
     }

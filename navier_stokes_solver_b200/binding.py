@@ -25,14 +25,14 @@ DA = dict(CELL_DOFS=(0, np.uint32), CELL_VERTICES=(1, np.float64), CELL_RANK=(2,
           L2G_U=(50, np.int64), L2G_P=(51, np.int64), CELL_GLOBAL=(52, np.int32), CELL_OWNED=(53, np.uint8),
           HALO_U_NBR=(60, np.int32), HALO_U_SEND_PTR=(61, np.int64), HALO_U_SEND_IDX=(62, np.int32), HALO_U_RECV_PTR=(63, np.int64),
           HALO_P_NBR=(64, np.int32), HALO_P_SEND_PTR=(65, np.int64), HALO_P_SEND_IDX=(66, np.int32), HALO_P_RECV_PTR=(67, np.int64))
-BLOCK_F, BLOCK_BT, BLOCK_B, BLOCK_MP, BLOCK_S, BLOCK_J = 0, 1, 2, 3, 4, 5
+BLOCK_F, BLOCK_BT, BLOCK_B, BLOCK_MP, BLOCK_S, BLOCK_J, BLOCK_F_DECOUPLED = 0, 1, 2, 3, 4, 5, 6
 MODE_STOKES, MODE_NEWTON, MODE_UNSTEADY_FIRST, MODE_UNSTEADY_NEWTON = 0, 1, 2, 3
 VEC_SOLUTION, VEC_SOLUTION_OLD, VEC_DELTA, VEC_RESIDUAL, VEC_EVAL, VEC_TMP0, VEC_TMP1 = 0, 1, 2, 3, 4, 5, 6
 STATIONARY, UNSTEADY = 0, 1
 NSX_OK, NSX_E_NOCONV, NSX_E_BADARG, NSX_E_CUDA, NSX_E_COMM, NSX_E_STATE = 0, 1, 2, 3, 4, 5
-OPT_ORDERING, OPT_VERBOSE, OPT_ORTHO, OPT_COOP_SWEEP, OPT_STREAM_SPMV, OPT_BLOCK_ROWS, OPT_HOST_INNER = 0, 1, 2, 3, 4, 5, 6
+OPT_ORDERING, OPT_VERBOSE, OPT_ORTHO, OPT_COOP_SWEEP, OPT_STREAM_SPMV, OPT_BLOCK_ROWS, OPT_HOST_INNER, OPT_DECOUPLE = 0, 1, 2, 3, 4, 5, 6, 7
 STAT = dict(INNER_F=0, INNER_S=1, PRECOND_APPLIES=2, KERNEL_LAUNCHES=3, LEVELS_F=4, LEVELS_MP=5, LEVELS_S=6,
-            SPMV_CALLS=7, ASSEMBLY_COLOURS=8, ASSEMBLY_TABLES=9, LAST_STEP=10, HALO_EXCHANGES=11, ALLREDUCES=12)
+            SPMV_CALLS=7, ASSEMBLY_COLOURS=8, ASSEMBLY_TABLES=9, LAST_STEP=10, HALO_EXCHANGES=11, ALLREDUCES=12, F_DECOUPLED=13)
 # every entry point include/nsx.h declares (tests check that the library exports each one)
 NSX_SYMBOLS = ["nsx_create", "nsx_destroy", "nsx_last_error", "nsx_set_option", "nsx_get_stat", "nsx_set_discretisation",
                "nsx_set_pattern", "nsx_set_faces", "nsx_set_dirichlet", "nsx_set_ranks", "nsx_finalize_setup",
@@ -41,7 +41,7 @@ NSX_SYMBOLS = ["nsx_create", "nsx_destroy", "nsx_last_error", "nsx_set_option", 
                "nsx_get_block_values", "nsx_set_block_values", "nsx_spmv", "nsx_inner_apply", "nsx_ilu0_factor",
                "nsx_schur", "nsx_precond_apply", "nsx_set_time_params", "nsx_time_kernel", "nsx_synchronize",
                "nsx_get_ordering", "nsx_set_partition", "nsx_set_halo", "nsx_comm_unique_id", "nsx_comm_init",
-               "nsx_halo_exchange", "nsx_vec_download_ghosts", "nsx_get_sweep_blocks"]
+               "nsx_halo_exchange", "nsx_vec_download_ghosts", "nsx_get_sweep_blocks", "nsx_check_decoupled"]
 NSX_HOST_SYMBOLS = ["nsx_disc_generate", "nsx_disc_from_gmsh", "nsx_disc_local", "nsx_disc_free", "nsx_host_last_error", "nsx_disc_info",
                     "nsx_disc_array", "nsx_disc_inlet_values"]
 
@@ -119,6 +119,7 @@ def nsx():
         L.nsx_synchronize.argtypes = [vp]
         L.nsx_get_ordering.argtypes = [vp, i32, vp]
         L.nsx_get_sweep_blocks.argtypes = [vp, i32, C.POINTER(i32), vp]
+        L.nsx_check_decoupled.argtypes = [vp, C.POINTER(i32)]
         L.nsx_set_partition.argtypes = [vp, i64, i64]
         L.nsx_set_halo.argtypes = [vp, i32, i32, vp, vp, vp, vp]
         L.nsx_comm_unique_id.argtypes = [vp]
@@ -422,10 +423,21 @@ class Device:
         return lu, perm
 
     def ordering(self, block):
-        nrows = self.n_u if block == BLOCK_F else self.n_p
+        nrows = self.n_u if block in (BLOCK_F, BLOCK_F_DECOUPLED) else self.n_p
         perm = np.empty(nrows, dtype=np.int32)
         self._ck(nsx().nsx_get_ordering(self.h, block, ptr(perm)))
         return perm
+
+    def decoupled(self):
+        """True when the current F has only exact zeros between the two velocity components: SGS sweeps and inner F products
+        then run on the same-component view (BLOCK_F_DECOUPLED)."""
+        yes = C.c_int32()
+        self._ck(nsx().nsx_check_decoupled(self.h, C.byref(yes)))
+        return bool(yes.value)
+
+    def sgs_block_id(self, block):
+        """the plan id an SGS application on `block` uses right now"""
+        return BLOCK_F_DECOUPLED if (block == BLOCK_F and self.decoupled()) else block
 
     def sweep_blocks(self, block):
         """(offsets, perm) of the block-local sweeps (ordering 2): block b eliminates perm[offsets[b]:offsets[b+1]] in that order;

@@ -184,6 +184,18 @@ struct Ctx {
   DevBuf<double> cell_vertices;
   DevBuf<uint32_t> cell_dofs;
   DevCSR F, Bt, B, Mp, S;
+  // Component-decoupled view of F (decouple.cu): in the Stokes-type branches the couplings between the two velocity
+  // components are exact zeros (the vector Laplacian is two scalar ones).  When the current values say so (checked on the
+  // device after every assembly), the SGS sweeps and the F products of the inner solves run on the same-component entries
+  // only -- half the bytes, bit-identical sums -- through Fd and the plan variant 1 of block F.
+  DevCSR Fd;
+  DevBuf<int64_t> Fd_src;          // Fd entry -> index into F.val
+  DevBuf<uint8_t> F_cross;         // per F entry: 1 = couples different components
+  DevBuf<unsigned long long> cross_count;
+  std::vector<uint8_t> h_comp_u;   // component of every local velocity dof (owned + ghost)
+  bool decouple = true;            // NSX_OPT_DECOUPLE
+  long long matrix_epoch = 1, dec_epoch = 0;   // F.val changed / decision taken at
+  bool dec_ok = false;
   std::vector<int64_t> owned_u{0, 0}, owned_p{0, 0};
   // Dirichlet
   DevBuf<uint32_t> bc_dof;
@@ -302,7 +314,8 @@ void assemble(Ctx &c, int mode, bool apply_inlet, double nu, double dt, double p
 void lift_drag(Ctx &c, double nu, double *drag, double *lift);
 
 // ---- trisolve.cu ----------------------------------------------------------------------------
-TriPlan &tri_plan(Ctx &c, int block);
+TriPlan &tri_plan(Ctx &c, int block, int variant = 0);   // variant 1 (block F only): same-component couplings only
+void gather_values(Ctx &c, int64_t nnz, const int64_t *src, const double *a, double *v);   // v[k] = a[src[k]]
 void tri_refresh_values(Ctx &c, TriPlan &P, const DevCSR &A);   // permuted copy of the values
 void ilu0_factor(Ctx &c, TriPlan &P, const DevCSR &A);
 void ilu0_apply(Ctx &c, TriPlan &P, double *y, const double *x);
@@ -311,13 +324,18 @@ DevCSR &block_ref(Ctx &c, int block);
 
 // ---- sweep_block.cu -------------------------------------------------------------------------
 // cuts the rows [lo, hi) of a square block into spatially compact groups (weighted recursive coordinate bisection of the
-// dof positions implied by the cell table); grp[i] = first_group + k
-int geometric_blocks(Ctx &c, int block, const DevCSR &A, int64_t lo, int64_t hi, int first_group, std::vector<int32_t> &grp);
+// dof positions implied by the cell table, weights = row lengths of `rowptr`); grp[i] = first_group + k
+int geometric_blocks(Ctx &c, int block, const std::vector<int64_t> &rowptr, int64_t lo, int64_t hi, int first_group, std::vector<int32_t> &grp);
 void bl_build(Ctx &c, TriPlan &P);                       // streams + descriptors of the block-local sweep
 void bl_refresh(Ctx &c, TriPlan &P, bool sgs);           // stream values from P.val (after tri_refresh_values / ilu0_factor)
 // y = M^-1 x.  Fused variants for the inner FGMRES: x is scaled by 1 / *scale on the way in and the scaled vector is
 // also stored to v_out; the launch does nothing when *gate != 0 (speculative launch behind a device-side decision).
 void bl_sweep(Ctx &c, TriPlan &P, bool sgs, double *y, const double *x, const double *scale = nullptr, double *v_out = nullptr, const int *gate = nullptr);
+
+// ---- decouple.cu ----------------------------------------------------------------------------
+const std::vector<uint8_t> &velocity_components(Ctx &c);
+// true when every cross-component entry of F is an exact zero right now (decision cached per assembly); refreshes Fd's values
+bool decoupled_ok(Ctx &c);
 
 // ---- spgemm.cu ------------------------------------------------------------------------------
 void schur_symbolic(Ctx &c);

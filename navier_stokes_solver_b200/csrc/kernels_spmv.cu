@@ -476,7 +476,7 @@ inline int pick_group(const DevCSR &A) {
 
 void spmv(Ctx &c, const DevCSR &A_, const double *x, double *y, bool add) {
   // ghost import of the input first (no-op on one GPU): a rank that owns no row of this block still has to post its sends
-  halo_exchange(c, (&A_ == &c.F || &A_ == &c.B) ? 0 : 1, x);
+  halo_exchange(c, (&A_ == &c.F || &A_ == &c.B || &A_ == &c.Fd) ? 0 : 1, x);
   if (!A_.nrows) return;
   spmv_local(c, A_, x, y, add);
 }

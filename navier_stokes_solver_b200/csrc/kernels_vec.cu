@@ -187,6 +187,131 @@ __global__ void __launch_bounds__(VT) k_multi_axpy_norm(VecList V, int k, const 
   }
 }
 
+// ---- wide variants for 16-byte aligned vectors: two elements per load, every vector of a chunk of 8 in flight at once --------
+// The Krylov vectors of the README size are 4.3 MB each: a pass over 1 + k of them is latency-bound unless every thread has all its
+// loads of a step in flight together.  One or two steps per thread, one reduction per chunk, 2 x #SMs CTAs of 512 threads.
+constexpr int DT = 512, KC = 8;
+
+__global__ void __launch_bounds__(DT, 2) k_multi_dot2(VecList V, int k, const double *__restrict__ w, int64_t n, double *partial, unsigned int *counter, double *result) {
+  __shared__ const double *sv[32];
+  __shared__ double sh[DT / 32][KC];
+  __shared__ bool last;
+  if (threadIdx.x < 32) sv[threadIdx.x] = V.v[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int64_t n2 = n >> 1;
+  const double2 *w2 = reinterpret_cast<const double2 *>(w);
+  for (int c0 = 0; c0 < k; c0 += KC) {
+    const int kc = min(KC, k - c0);
+    double acc[KC];
+#pragma unroll
+    for (int m = 0; m < KC; ++m) acc[m] = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)DT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * DT) {
+      const double2 wv = w2[i];
+      double2 vv[KC];
+#pragma unroll
+      for (int m = 0; m < KC; ++m) vv[m] = m < kc ? reinterpret_cast<const double2 *>(sv[c0 + m])[i] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int m = 0; m < KC; ++m) acc[m] = fma(wv.y, vv[m].y, fma(wv.x, vv[m].x, acc[m]));
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+      const double wl = w[n - 1];
+#pragma unroll
+      for (int m = 0; m < KC; ++m) if (m < kc) acc[m] = fma(wl, sv[c0 + m][n - 1], acc[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < KC; ++m) {
+      const double r = warp_sum(acc[m]);
+      if (lane == 0) sh[wp][m] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < kc) {
+      double r = 0;
+#pragma unroll
+      for (int q = 0; q < DT / 32; ++q) r += sh[q][threadIdx.x];
+      partial[(size_t)blockIdx.x * 32 + c0 + threadIdx.x] = r;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicInc(counter, gridDim.x - 1);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    for (int m = wp; m < k; m += DT / 32) {
+      double r = 0;
+      for (int b = lane; b < gridDim.x; b += 32) r += __ldcg(&partial[(size_t)b * 32 + m]);
+      r = warp_sum(r);
+      if (lane == 0) result[m] = r;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DT, 2) k_multi_axpy_norm2(VecList V, int k, const double *coef, double *__restrict__ w, int64_t n, double *partial,
+                                                         unsigned int *counter, double *norm2) {
+  __shared__ const double *sv[32];
+  __shared__ double sc[32];
+  __shared__ double sh[DT / 32];
+  __shared__ bool last;
+  if (threadIdx.x < 32) { sv[threadIdx.x] = V.v[threadIdx.x]; sc[threadIdx.x] = threadIdx.x < k ? coef[threadIdx.x] : 0.0; }
+  __syncthreads();
+  const int64_t n2 = n >> 1;
+  double2 *w2 = reinterpret_cast<double2 *>(w);
+  double acc = 0;
+  for (int64_t i = blockIdx.x * (int64_t)DT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * DT) {
+    double2 wv = w2[i];
+    for (int m0 = 0; m0 < k; m0 += KC) {
+      double2 vv[KC];
+#pragma unroll
+      for (int m = 0; m < KC; ++m) vv[m] = m0 + m < k ? reinterpret_cast<const double2 *>(sv[m0 + m])[i] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int m = 0; m < KC; ++m) {   // coefficients beyond k are zero: same order of subtractions as the narrow kernel
+        const double cm = sc[(m0 + m) & 31];
+        if (m0 + m < k) { wv.x -= cm * vv[m].x; wv.y -= cm * vv[m].y; }
+      }
+    }
+    w2[i] = wv;
+    acc += wv.x * wv.x + wv.y * wv.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    double wl = w[n - 1];
+    for (int m = 0; m < k; ++m) wl -= sc[m] * sv[m][n - 1];
+    w[n - 1] = wl;
+    acc += wl * wl;
+  }
+  // block sum over DT threads
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+#pragma unroll
+    for (int q = 0; q < DT / 32; ++q) s += sh[q];
+    partial[(size_t)blockIdx.x * 32] = s;
+    __threadfence();
+    const unsigned int t = atomicInc(counter, gridDim.x - 1);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double r = 0;
+    for (int i = threadIdx.x; i < gridDim.x; i += DT) r += __ldcg(&partial[(size_t)i * 32]);
+    r = warp_sum(r);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0;
+#pragma unroll
+      for (int q = 0; q < DT / 32; ++q) s += sh[q];
+      *norm2 = s;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(VT) k_scale_to(double *__restrict__ v, const double *__restrict__ x, const double *a, const int *gate, int64_t n) {
   if (gate && *gate != 0) return;
   const double av = *a;
@@ -229,55 +354,81 @@ __global__ void k_fg_begin(FgDev *st, const double *beta2, double tol, int max_i
   fg_publish(st, rec, seq);
 }
 
-__global__ void k_fg_step(FgDev *st, const double *slots, int j, int mode, FgRec *rec, long long seq) {
-  if (st->gate >= 2) { fg_publish(st, rec, seq); return; }
-  double *col = st->R[j];
-  double nrm2;
-  if (mode == 0) {
-    for (int i = 0; i <= j; ++i) col[i] = slots[i];
-    nrm2 = slots[j + 1];
-  } else if (mode == 1) {
-    double h2 = 0;
-    for (int i = 0; i <= j; ++i) { col[i] = slots[i]; h2 += slots[i] * slots[i]; }
-    nrm2 = slots[64];
-    if (nrm2 < 0.01 * (nrm2 + h2)) { st->gate = 1; fg_publish(st, rec, seq); return; }
-  } else {
-    for (int i = 0; i <= j; ++i) col[i] = (mode == 2 ? col[i] : slots[i]) + slots[32 + i];
-    nrm2 = slots[65];
+// One warp: the inputs are fetched in parallel into shared memory, lane 0 runs the short sequential recurrences there.
+__global__ void __launch_bounds__(32) k_fg_step(FgDev *st, const double *slots, int j, int mode, FgRec *rec, long long seq) {
+  __shared__ double col[34], cs[32], sn[32], g[34], h2s[32];
+  const int lane = threadIdx.x;
+  if (st->gate >= 2) { if (lane == 0) fg_publish(st, rec, seq); return; }
+  // gather: coefficients of this column, the rotations so far, the rotated right-hand side
+  {
+    double v = 0.0;
+    if (lane <= j) {
+      if (mode == 0 || mode == 1) v = slots[lane];
+      else v = (mode == 2 ? st->R[j][lane] : slots[lane]) + slots[32 + lane];
+    }
+    col[lane] = v;
+    h2s[lane] = lane <= j ? v * v : 0.0;
+    cs[lane] = lane < j ? st->cs[lane] : 0.0;
+    sn[lane] = lane < j ? st->sn[lane] : 0.0;
+    g[lane] = lane <= j ? st->g[lane] : 0.0;
   }
-  st->gate = 0;
+  __syncwarp();
+  const double nrm2 = mode == 0 ? slots[j + 1] : (mode == 1 ? slots[64] : slots[65]);
+  if (mode == 1) {
+    double h2 = 0;
+    for (int i = 0; i <= j; ++i) h2 += h2s[i];   // same order on every lane
+    if (nrm2 < 0.01 * (nrm2 + h2)) {            // heavy cancellation: keep the first-pass coefficients, ask for a second pass
+      if (lane <= j) st->R[j][lane] = col[lane];
+      __syncwarp();
+      if (lane == 0) { st->gate = 1; fg_publish(st, rec, seq); }
+      return;
+    }
+  }
   const double a = sqrt(nrm2);
-  st->a = a;
   int verdict = 0;
+  double res = st->res;
+  int it = st->it;
   if (j > 0) {
-    st->res = fabs(st->g[j]);
-    verdict = fg_check(st, ++st->it, st->res);
+    res = fabs(g[j]);
+    verdict = fg_check(st, ++it, res);
   }
   if (verdict != 0 || j == 29) {   // y of the (j+1) x j least-squares problem: back substitution in the rotated columns
+    // lane cc keeps y[cc]; row i: y[i] = (g[i] - sum_{cc > i} R[cc][i] y[cc]) / R[i][i]
+    double ycc = 0.0;
     for (int i = j - 1; i >= 0; --i) {
-      double s = st->g[i];
-      for (int cc = i + 1; cc < j; ++cc) s -= st->R[cc][i] * st->y[cc];
-      st->y[i] = s / st->R[i][i];
+      double t = (lane > i && lane < j) ? st->R[lane][i] * ycc : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      const double yi = (g[i] - t) / st->R[i][i];
+      if (lane == i) ycc = yi;
     }
-    st->ny = j;
-    st->gate = verdict;
-    if (verdict == 0 && j == 29) st->gate = 0;
-    fg_publish(st, rec, seq);
+    if (lane < j) st->y[lane] = ycc;
+    __syncwarp();
+    if (lane == 0) {
+      st->a = a; st->res = res; st->it = it; st->ny = j; st->gate = verdict;
+      fg_publish(st, rec, seq);
+    }
     return;
   }
-  col[j + 1] = a;
-  for (int i = 0; i < j; ++i) {
-    const double t = st->cs[i] * col[i] + st->sn[i] * col[i + 1];
-    col[i + 1] = -st->sn[i] * col[i] + st->cs[i] * col[i + 1];
-    col[i] = t;
+  if (lane == 0) {
+    col[j + 1] = a;
+    for (int i = 0; i < j; ++i) {
+      const double t = cs[i] * col[i] + sn[i] * col[i + 1];
+      col[i + 1] = -sn[i] * col[i] + cs[i] * col[i + 1];
+      col[i] = t;
+    }
+    const double r = 1.0 / sqrt(col[j] * col[j] + col[j + 1] * col[j + 1]);
+    const double snj = col[j + 1] * r, csj = col[j] * r;
+    col[j] = csj * col[j] + snj * col[j + 1];
+    st->sn[j] = snj; st->cs[j] = csj;
+    st->g[j + 1] = -snj * g[j];
+    st->g[j] = csj * g[j];
+    st->a = a; st->res = res; st->it = it; st->gate = 0;
   }
-  const double r = 1.0 / sqrt(col[j] * col[j] + col[j + 1] * col[j + 1]);
-  st->sn[j] = col[j + 1] * r;
-  st->cs[j] = col[j] * r;
-  col[j] = st->cs[j] * col[j] + st->sn[j] * col[j + 1];
-  st->g[j + 1] = -st->sn[j] * st->g[j];
-  st->g[j] *= st->cs[j];
-  fg_publish(st, rec, seq);
+  __syncwarp();
+  if (lane <= j) st->R[j][lane] = col[lane];
+  __syncwarp();
+  if (lane == 0) fg_publish(st, rec, seq);
 }
 
 }  // namespace
@@ -300,7 +451,7 @@ void fg_begin(Ctx &c, const double *beta2, double tol, int max_it, int it0) {
 }
 void fg_step(Ctx &c, const double *slots, int j, int mode) {
   FgDev *st = fg_state(c);
-  k_fg_step<<<1, 1, 0, c.stream>>>(st, slots, j, mode, (FgRec *)c.fg_rec, ++c.fg_seq); LAUNCHED(c);
+  k_fg_step<<<1, 32, 0, c.stream>>>(st, slots, j, mode, (FgRec *)c.fg_rec, ++c.fg_seq); LAUNCHED(c);
 }
 FgRec fg_wait(Ctx &c) {
   const FgRec *rec = (const FgRec *)c.fg_rec;
@@ -356,20 +507,30 @@ void vec_equ(Ctx &c, double *y, double a, const double *x, int64_t n) {
   k_equ<<<vgrid(c, n), VT, 0, c.stream>>>(y, a, x, n); LAUNCHED(c);
 }
 
-double *slot_ptr(Ctx &c, int slot) { return c.red_result.p + slot; }
-
 static void ensure_red(Ctx &c);
+
+double *slot_ptr(Ctx &c, int slot) { ensure_red(c); return c.red_result.p + slot; }
+
+// the wide kernels need 16-byte aligned vectors and pay off once a vector spans a few CTAs
+static bool wide_ok(const VecList &V, int k, const double *w, int64_t n) {
+  if (n < 8192 || ((uintptr_t)w & 15)) return false;
+  for (int m = 0; m < k; ++m) if ((uintptr_t)V.v[m] & 15) return false;
+  return true;
+}
+static int wide_grid(Ctx &c, int64_t n) { return grid_for(n >> 1, DT, c.num_sms * 2); }
 
 void vec_multi_dot_dev(Ctx &c, int slot0, const VecList &V, int k, const double *w, int64_t n) {
   ensure_red(c);
   if (k < 1 || k > 31) throw std::invalid_argument("multi-dot handles 1..31 vectors");
-  k_multi_dot<<<vgrid(c, n), VT, 0, c.stream>>>(V, k, w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot0));
+  if (wide_ok(V, k, w, n)) k_multi_dot2<<<wide_grid(c, n), DT, 0, c.stream>>>(V, k, w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot0));
+  else k_multi_dot<<<vgrid(c, n), VT, 0, c.stream>>>(V, k, w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot0));
   LAUNCHED(c);
   allreduce_slots(c, slot0, k);
 }
 void vec_multi_axpy_norm_dev(Ctx &c, int slot_norm, const VecList &V, int k, int slot_coef, double *w, int64_t n) {
   ensure_red(c);
-  k_multi_axpy_norm<<<vgrid(c, n), VT, 0, c.stream>>>(V, k, slot_ptr(c, slot_coef), w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot_norm));
+  if (wide_ok(V, k, w, n)) k_multi_axpy_norm2<<<wide_grid(c, n), DT, 0, c.stream>>>(V, k, slot_ptr(c, slot_coef), w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot_norm));
+  else k_multi_axpy_norm<<<vgrid(c, n), VT, 0, c.stream>>>(V, k, slot_ptr(c, slot_coef), w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot_norm));
   LAUNCHED(c);
   allreduce_slots(c, slot_norm, 1);
 }

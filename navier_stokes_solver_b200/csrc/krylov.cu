@@ -459,11 +459,15 @@ struct Preconditioner {
   // the initialize() calls of solve_system: every inner preconditioner is rebuilt from the
   // current matrix values (NSSolverStationary.cpp:583-585, 601-604, 620-626)
   void initialize() {
-    opF = [this](double *y, const double *x) { spmv(c, c.F, x, y); };
+    // F products of the inner solves: on the same-component entries only while the cross-component ones are exact zeros
+    const bool dec = decoupled_ok(c);
+    if (dec) opF = [this](double *y, const double *x) { spmv(c, c.Fd, x, y); };
+    else opF = [this](double *y, const double *x) { spmv(c, c.F, x, y); };
     opM = [this](double *y, const double *x) { spmv(c, c.Mp, x, y); };
     opS = [this](double *y, const double *x) { spmv(c, c.S, x, y); };
     if (type == 0) {
-      F = &tri_plan(c, NSX_BLOCK_F); Mp = &tri_plan(c, NSX_BLOCK_MP);
+      // Gauss-Seidel sweeps skip exact zeros too (plan variant 1); ILU(0) needs the full pattern (fill lands on those entries)
+      F = &tri_plan(c, NSX_BLOCK_F, (flavour == NSX_STATIONARY && dec) ? 1 : 0); Mp = &tri_plan(c, NSX_BLOCK_MP);
       if (flavour == NSX_STATIONARY) { tri_refresh_values(c, *F, c.F); tri_refresh_values(c, *Mp, c.Mp); }
       else { ilu0_factor(c, *F, c.F); ilu0_factor(c, *Mp, c.Mp); }
     } else if (type == 1) {

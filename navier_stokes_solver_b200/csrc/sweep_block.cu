@@ -186,7 +186,7 @@ void rcb(std::vector<Pt> &pts, int64_t lo, int64_t hi, int parts, int first, std
 
 }  // namespace
 
-int geometric_blocks(Ctx &c, int block, const DevCSR &A, int64_t lo, int64_t hi, int first_group, std::vector<int32_t> &grp) {
+int geometric_blocks(Ctx &c, int block, const std::vector<int64_t> &rowptr, int64_t lo, int64_t hi, int first_group, std::vector<int32_t> &grp) {
   const int64_t n = hi - lo;
   const bool pressure = block != NSX_BLOCK_F;
   const int64_t off = pressure ? c.n_u + c.n_ug : 0;           // position of the block's dofs in the cell table's numbering
@@ -208,7 +208,7 @@ int geometric_blocks(Ctx &c, int block, const DevCSR &A, int64_t lo, int64_t hi,
   std::vector<Pt> pts(n);
   for (int64_t i = 0; i < n; ++i) {
     const double m = cnt[i] ? 1.0 / cnt[i] : 0.0;
-    pts[i] = Pt{sx[i] * m, sy[i] * m, (double)(A.h_rowptr[lo + i + 1] - A.h_rowptr[lo + i]), (int32_t)(lo + i)};
+    pts[i] = Pt{sx[i] * m, sy[i] * m, (double)(rowptr[lo + i + 1] - rowptr[lo + i]), (int32_t)(lo + i)};
   }
   // one block per SM while that gives blocks of 512 .. 4096 rows; fewer blocks below, whole waves of blocks above (the
   // weights are non-zero counts, so a block of short rows may hold more rows than the average: MAX_BLOCK_ROWS leaves room)

@@ -449,12 +449,41 @@ DevCSR &block_ref(Ctx &c, int block) {
   throw std::invalid_argument("unknown block id");
 }
 
-TriPlan &tri_plan(Ctx &c, int block) {
-  auto it = c.tri.find(block);
+TriPlan &tri_plan(Ctx &c, int block, int variant) {
+  if (variant && block != NSX_BLOCK_F) throw std::invalid_argument("only block F has a component-decoupled plan");
+  const int key = block + 16 * variant;
+  auto it = c.tri.find(key);
   if (it != c.tri.end() && it->second->ordering == c.ordering) return *it->second;
-  const DevCSR &A = block_ref(c, block);
-  if (A.nrows > A.ncols) throw std::invalid_argument("triangular plan needs a square block (owned rows x owned + ghost columns on a partitioned system)");
-  if (A.h_rowptr.empty()) throw std::logic_error("block pattern is not set");
+  const DevCSR &A0 = block_ref(c, block);
+  if (A0.nrows > A0.ncols) throw std::invalid_argument("triangular plan needs a square block (owned rows x owned + ghost columns on a partitioned system)");
+  if (A0.h_rowptr.empty()) throw std::logic_error("block pattern is not set");
+  // The pattern the plan is built from: the block's own, or (variant 1) its same-component entries only.  `A` is a light
+  // view (host pattern + sizes); orig[k] is the position of entry k in the block's value array.
+  struct View {
+    int64_t nrows, ncols;
+    std::vector<int64_t> own_rp, orig;
+    std::vector<int32_t> own_col;
+    const std::vector<int64_t> *rp;
+    const std::vector<int32_t> *col;
+  } V;
+  V.nrows = A0.nrows; V.ncols = A0.ncols; V.rp = &A0.h_rowptr; V.col = &A0.h_col;
+  if (variant) {
+    const std::vector<uint8_t> &comp = velocity_components(c);
+    V.own_rp.assign(A0.nrows + 1, 0);
+    for (int64_t i = 0; i < A0.nrows; ++i) {
+      int64_t cnt = 0;
+      for (int64_t k = A0.h_rowptr[i]; k < A0.h_rowptr[i + 1]; ++k) cnt += comp[A0.h_col[k]] == comp[i];
+      V.own_rp[i + 1] = V.own_rp[i] + cnt;
+    }
+    V.own_col.resize(V.own_rp[A0.nrows]); V.orig.resize(V.own_rp[A0.nrows]);
+    for (int64_t i = 0; i < A0.nrows; ++i) {
+      int64_t o = V.own_rp[i];
+      for (int64_t k = A0.h_rowptr[i]; k < A0.h_rowptr[i + 1]; ++k)
+        if (comp[A0.h_col[k]] == comp[i]) { V.own_col[o] = A0.h_col[k]; V.orig[o] = k; ++o; }
+    }
+    V.rp = &V.own_rp; V.col = &V.own_col;
+  }
+  struct { int64_t nrows, ncols; const std::vector<int64_t> &h_rowptr; const std::vector<int32_t> &h_col; } A{V.nrows, V.ncols, *V.rp, *V.col};
   const std::vector<int64_t> &owned = (block == NSX_BLOCK_F) ? c.owned_u : c.owned_p;
   std::unique_ptr<TriPlan> up(new TriPlan);
   TriPlan &P = *up;
@@ -469,7 +498,7 @@ TriPlan &tri_plan(Ctx &c, int block) {
   if (c.ordering == 2) {
     int ng = 0;
     for (size_t r = 0; r + 1 < owned.size(); ++r)
-      if (owned[r + 1] > owned[r]) ng += geometric_blocks(c, block, A, owned[r], owned[r + 1], ng, range);
+      if (owned[r + 1] > owned[r]) ng += geometric_blocks(c, block, A.h_rowptr, owned[r], owned[r + 1], ng, range);
     P.nblk = ng;
   } else {
     for (size_t r = 0; r + 1 < owned.size(); ++r)
@@ -565,7 +594,7 @@ TriPlan &tri_plan(Ctx &c, int block) {
       int64_t o = P.h_rowptr[r];
       for (auto &t : tmp) {
         if (t.first == r) P.h_diag[r] = (int32_t)(o - P.h_rowptr[r]);
-        P.h_col[o] = t.first; src[o] = t.second; ++o;
+        P.h_col[o] = t.first; src[o] = V.orig.empty() ? t.second : V.orig[t.second]; ++o;
       }
     }
   }
@@ -603,8 +632,14 @@ TriPlan &tri_plan(Ctx &c, int block) {
   P.yp.alloc(n);
   if (P.nblk) bl_build(c, P);
   NSX_CUDA(cudaStreamSynchronize(c.stream));
-  c.tri[block] = std::move(up);
-  return *c.tri[block];
+  c.tri[key] = std::move(up);
+  return *c.tri[key];
+}
+
+void gather_values(Ctx &c, int64_t nnz, const int64_t *src, const double *a, double *v) {
+  if (!nnz) return;
+  k_gather_values<<<grid_for(nnz, 256, c.num_sms * 16), 256, 0, c.stream>>>(nnz, src, a, v);
+  c.stat_launches++;
 }
 
 void tri_refresh_values(Ctx &c, TriPlan &P, const DevCSR &A) {
