@@ -126,6 +126,12 @@ int nsx_vec_copy(nsx_ctx *ctx, int dst, int src);
  * solution (and solution_old), then the Dirichlet rows; returns ||r||_2 (the l2_norm() the Newton
  * loop takes next, NSSolverStationary.cpp:698). */
 int nsx_assemble(nsx_ctx *ctx, int mode, int apply_inlet, double nu, double dt, double p_out, double *residual_l2);
+/* The residual of assemble_system alone, for the line search (NSSolverStationary.cpp:718-735, NSSolver.cpp:727-740): the reference
+ * re-assembles J, Mp and r for every trial step length and only takes ||r||; its Newton loop assembles again before the next
+ * solve, so the matrices of the trial assemblies are never read.  This call leaves in `residual` (and in the Dirichlet entries
+ * of `delta`) exactly the bits nsx_assemble(mode, apply_inlet = 0, ...) would, and does not touch the matrices, which therefore
+ * still belong to the previous state until the next nsx_assemble. */
+int nsx_assemble_residual(nsx_ctx *ctx, int mode, double nu, double dt, double p_out, double *residual_l2);
 /* solve_system (NSSolverStationary.cpp:579-647, NSSolver.cpp:601-672): solver 0 GMRES / 1 FGMRES /
  * 2 BiCGStab; prec 0 blockDiagonal / 1 blockTriangular / 2 aSIMPLE; delta is the warm start. */
 int nsx_solve(nsx_ctx *ctx, int flavour, int solver, int prec, double tol, int max_it, double alpha,

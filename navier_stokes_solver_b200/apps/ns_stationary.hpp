@@ -79,6 +79,15 @@ class NSSolverStationary {
     check(prob.ctx, nsx_assemble(prob.ctx, mode, global_first_iter ? 1 : 0, nu, 0.0, p_out, &last_residual_norm), "nsx_assemble");
   }
 
+  // The line search's assembly (NSSolverStationary.cpp:724-727): the reference re-assembles everything for a norm; the matrices of
+  // those assemblies are never read (the loop assembles again before the next solve), so by default only the residual is
+  // formed -- bit-identical ||r||.  NSX_FULL_LINESEARCH_ASSEMBLY=1 restores the full assembly.
+  void assemble_for_line_search(bool computing_stokes) {
+    static const bool full = [] { const char *e = std::getenv("NSX_FULL_LINESEARCH_ASSEMBLY"); return e && e[0] == '1'; }();
+    if (full) { assemble_system(false, computing_stokes); return; }
+    check(prob.ctx, nsx_assemble_residual(prob.ctx, computing_stokes ? NSX_MODE_STOKES : NSX_MODE_NEWTON, nu, 0.0, p_out, &last_residual_norm), "nsx_assemble_residual");
+  }
+
   // NSSolverStationary.cpp:579-647
   int solve_system() {
     int it = 0;
@@ -123,7 +132,7 @@ class NSSolverStationary {
             check(prob.ctx, nsx_save_eval_point(prob.ctx), "nsx_save_eval_point");
             for (double alpha = 1; alpha > 1e-12; alpha *= 0.1) {
               check(prob.ctx, nsx_update(prob.ctx, alpha), "nsx_update");
-              assemble_system(false, computing_stokes);
+              assemble_for_line_search(computing_stokes);
               residual_norm = last_residual_norm;
               pcout << "  Evaluating alpha=" << alpha << ", ||r||=" << residual_norm << std::endl;
               if (residual_norm < prev_residual) break;

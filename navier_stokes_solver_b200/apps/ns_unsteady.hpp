@@ -62,12 +62,19 @@ class NSSolver {
                                  p_out, &last_residual_norm), "nsx_assemble");
   }
 
+  // line-search assembly (NSSolver.cpp:733-736): residual only by default, see ns_stationary.hpp
+  void assemble_for_line_search() {
+    static const bool full = [] { const char *e = std::getenv("NSX_FULL_LINESEARCH_ASSEMBLY"); return e && e[0] == '1'; }();
+    if (full) { assemble_system(false); return; }
+    check(prob.ctx, nsx_assemble_residual(prob.ctx, NSX_MODE_UNSTEADY_NEWTON, nu, deltat, p_out, &last_residual_norm), "nsx_assemble_residual");
+  }
+
   // NSSolver.cpp:601-672
   int solve_system() {
     int it = 0;
     double res = 0;
     check(prob.ctx, nsx_solve(prob.ctx, NSX_UNSTEADY, solver_type, preconditioner_type, tolerance, 100000, 0.5, &it, &res), "nsx_solve");
-    pcout << "   " << it << " solver iterations" << std::endl;
+    pcout << "   " << it << " iterations" << std::endl;   // NSSolver.cpp:670 (the stationary binary says "solver iterations")
     return it;
   }
 
@@ -100,7 +107,7 @@ class NSSolver {
           check(prob.ctx, nsx_save_eval_point(prob.ctx), "nsx_save_eval_point");
           for (double alpha = 1; alpha > 1e-12; alpha *= 0.1) {
             check(prob.ctx, nsx_update(prob.ctx, alpha), "nsx_update");
-            assemble_system(false);
+            assemble_for_line_search();
             residual_norm = last_residual_norm;
             pcout << "  Evaluating alpha=" << alpha << ", ||r||=" << residual_norm << std::endl;
             if (residual_norm <= prev_residual) break;

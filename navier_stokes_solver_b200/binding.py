@@ -36,7 +36,7 @@ STAT = dict(INNER_F=0, INNER_S=1, PRECOND_APPLIES=2, KERNEL_LAUNCHES=3, LEVELS_F
 # every entry point include/nsx.h declares (tests check that the library exports each one)
 NSX_SYMBOLS = ["nsx_create", "nsx_destroy", "nsx_last_error", "nsx_set_option", "nsx_get_stat", "nsx_set_discretisation",
                "nsx_set_pattern", "nsx_set_faces", "nsx_set_dirichlet", "nsx_set_ranks", "nsx_finalize_setup",
-               "nsx_vec_upload", "nsx_vec_download", "nsx_vec_set", "nsx_vec_copy", "nsx_assemble", "nsx_solve", "nsx_save_eval_point", "nsx_update",
+               "nsx_vec_upload", "nsx_vec_download", "nsx_vec_set", "nsx_vec_copy", "nsx_assemble", "nsx_assemble_residual", "nsx_solve", "nsx_save_eval_point", "nsx_update",
                "nsx_copy_old", "nsx_lift_drag", "nsx_assemble_cells", "nsx_get_block_nnz", "nsx_get_block_pattern",
                "nsx_get_block_values", "nsx_set_block_values", "nsx_spmv", "nsx_inner_apply", "nsx_ilu0_factor",
                "nsx_schur", "nsx_precond_apply", "nsx_set_time_params", "nsx_time_kernel", "nsx_synchronize",
@@ -100,6 +100,7 @@ def nsx():
         L.nsx_vec_copy.argtypes = [vp, i32, i32]
         L.nsx_assemble.argtypes = [vp, i32, i32, dbl, dbl, dbl, c_dp]
         L.nsx_assemble_cells.argtypes = [vp, i32, dbl, dbl, dbl]
+        L.nsx_assemble_residual.argtypes = [vp, i32, dbl, dbl, dbl, c_dp]
         L.nsx_solve.argtypes = [vp, i32, i32, i32, dbl, i32, dbl, C.POINTER(i32), c_dp]
         L.nsx_save_eval_point.argtypes = [vp]
         L.nsx_update.argtypes = [vp, dbl]
@@ -343,6 +344,12 @@ class Device:
 
     def assemble_cells(self, mode, nu, dt=0.01, p_out=1.0):
         self._ck(nsx().nsx_assemble_cells(self.h, mode, nu, dt, p_out))
+
+    def assemble_residual(self, mode, nu, dt=0.01, p_out=1.0):
+        """||r|| of a full assembly with homogeneous Dirichlet values, matrices untouched (line-search trials)"""
+        r = C.c_double()
+        self._ck(nsx().nsx_assemble_residual(self.h, mode, nu, dt, p_out, C.byref(r)))
+        return r.value
 
     def solve(self, flavour, solver, prec, tol, max_it=20000, alpha=0.5):
         it, fr = C.c_int(), C.c_double()

@@ -212,6 +212,7 @@ namespace {
 
 struct AsmArgs {
   int mode;
+  int res_only;   // 1: residual contributions only (the matrices are left alone)
   double nu, inv_dt;
   const double *sol, *sol_old;
   double *res;
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(TPC *CPB) k_assemble(const AsmArgs A) {
     if (active) {
       const uint16_t *off = A.pat_off + (int64_t)A.cell_pat[cell] * (ND * ND);
       // ---- F: node pairs ----
-      for (int pr = lt; pr < NVN * NVN; pr += TPC) {
+      for (int pr = lt; pr < (A.res_only ? 0 : NVN * NVN); pr += TPC) {
         const int a = pr / NVN, b = pr % NVN;
         double fb = 0, f00 = 0, f01 = 0, f10 = 0, f11 = 0;
         if (newton) {
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(TPC *CPB) k_assemble(const AsmArgs A) {
         if (f10 != 0.0) A.F_val[srb0[slot][i1] + off[i1 * ND + j0]] += f10;
       }
       // ---- Bt and B: (velocity node, component) x pressure node ----
-      for (int e = lt; e < NVN * 2 * NPN; e += TPC) {
+      for (int e = lt; e < (A.res_only ? 0 : NVN * 2 * NPN); e += TPC) {
         const int m = e % NPN, ac = e / NPN, a = ac / 2, cc = ac % 2;
         double s = 0;
 #pragma unroll
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(TPC *CPB) k_assemble(const AsmArgs A) {
         A.B_val[srb0[slot][j] + off[j * ND + i]] += newton ? s : -s;
       }
       // ---- Mp ----
-      for (int e = lt; e < NPN * NPN; e += TPC) {
+      for (int e = lt; e < (A.res_only ? 0 : NPN * NPN); e += TPC) {
         const int m = e / NPN, k = e % NPN;
         double s = 0;
 #pragma unroll
@@ -515,11 +516,11 @@ __global__ void k_lift_drag(int64_t nfaces, const int32_t *fcell, const int32_t 
 
 }  // namespace
 
-void assemble_cells(Ctx &c, int mode, double nu, double dt, double p_out) {
-  c.F.val.zero(c.stream); c.Bt.val.zero(c.stream); c.B.val.zero(c.stream); c.Mp.val.zero(c.stream);
+void assemble_cells(Ctx &c, int mode, double nu, double dt, double p_out, bool res_only) {
+  if (!res_only) { c.F.val.zero(c.stream); c.Bt.val.zero(c.stream); c.B.val.zero(c.stream); c.Mp.val.zero(c.stream); }
   c.vec[NSX_VEC_RESIDUAL].zero(c.stream);
   AsmArgs A;
-  A.mode = mode; A.nu = nu; A.inv_dt = (dt != 0.0) ? 1.0 / dt : 0.0;
+  A.mode = mode; A.res_only = res_only ? 1 : 0; A.nu = nu; A.inv_dt = (dt != 0.0) ? 1.0 / dt : 0.0;
   A.sol = c.vec[NSX_VEC_SOLUTION].p; A.sol_old = c.vec[NSX_VEC_SOLUTION_OLD].p; A.res = c.vec[NSX_VEC_RESIDUAL].p;
   A.F_rp = c.F.rowptr.p; A.Bt_rp = c.Bt.rowptr.p; A.B_rp = c.B.rowptr.p; A.Mp_rp = c.Mp.rowptr.p;
   A.F_val = c.F.val.p; A.Bt_val = c.Bt.val.p; A.B_val = c.B.val.p; A.Mp_val = c.Mp.val.p;
@@ -529,7 +530,9 @@ void assemble_cells(Ctx &c, int mode, double nu, double dt, double p_out) {
   // ghost import of the state the cells read (`solution = solution_owned`, NSSolverStationary.cpp:722)
   halo_exchange(c, 0, A.sol); halo_exchange(c, 1, A.sol + c.n_u);
   if (mode >= NSX_MODE_UNSTEADY_FIRST) { halo_exchange(c, 0, A.sol_old); halo_exchange(c, 1, A.sol_old + c.n_u); }
-  for (int col = 0; col < c.ncolors; ++col) {
+  // the Stokes-type branches skip the residual body (NSSolverStationary.cpp:455-458): nothing for the cells to do
+  const bool cells_idle = res_only && (mode == NSX_MODE_STOKES || mode == NSX_MODE_UNSTEADY_FIRST);
+  for (int col = 0; col < c.ncolors && !cells_idle; ++col) {
     const int64_t lo = c.color_ptr[col], hi = c.color_ptr[col + 1];
     if (hi == lo) continue;
     A.cells = c.color_cells.p + lo; A.ncells = (int)(hi - lo);
@@ -564,8 +567,27 @@ void apply_boundary_values(Ctx &c, bool apply_inlet) {
 }
 
 void assemble(Ctx &c, int mode, bool apply_inlet, double nu, double dt, double p_out) {
-  assemble_cells(c, mode, nu, dt, p_out);
+  assemble_cells(c, mode, nu, dt, p_out, false);
   apply_boundary_values(c, apply_inlet);
+}
+
+namespace {
+// what apply_boundary_values leaves in the vectors for homogeneous values: delta[i] = 0, r[i] = 0 * diagonal
+__global__ void k_bc_vectors(int64_t nbc, const uint32_t *bc_dof, double *delta, double *res) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b < nbc) { delta[bc_dof[b]] = 0.0; res[bc_dof[b]] = 0.0; }
+}
+}  // namespace
+
+// The residual vector a full assembly with homogeneous Dirichlet values would leave, bit for bit (same kernel, same colour
+// order), without touching J or Mp: what the line search needs (NSSolverStationary.cpp:724-729 re-assembles everything for
+// a norm; the matrices of those assemblies are never used -- the Newton loop assembles again before the next solve).
+void assemble_residual(Ctx &c, int mode, double nu, double dt, double p_out) {
+  assemble_cells(c, mode, nu, dt, p_out, true);
+  if (c.nbc) {
+    k_bc_vectors<<<(int)((c.nbc + 255) / 256), 256, 0, c.stream>>>(c.nbc, c.bc_dof.p, c.vec[NSX_VEC_DELTA].p, c.vec[NSX_VEC_RESIDUAL].p);
+    c.stat_launches++;
+  }
 }
 
 void lift_drag(Ctx &c, double nu, double *drag, double *lift) {

@@ -367,6 +367,18 @@ int nsx_assemble(nsx_ctx *ctx, int mode, int apply_inlet, double nu, double dt, 
   });
 }
 
+int nsx_assemble_residual(nsx_ctx *ctx, int mode, double nu, double dt, double p_out, double *residual_l2) {
+  return guarded(ctx, [&] {
+    Ctx &c = *ctx;
+    need_final(c);
+    if (mode < NSX_MODE_STOKES || mode > NSX_MODE_UNSTEADY_NEWTON) throw std::invalid_argument("unknown assembly mode");
+    if (!(nu > 0.0)) throw std::invalid_argument("nu must be positive");
+    if (mode >= NSX_MODE_UNSTEADY_FIRST && !(dt > 0.0)) throw std::invalid_argument("dt must be positive");
+    assemble_residual(c, mode, nu, dt, p_out);
+    if (residual_l2) *residual_l2 = vec_norm(c, c.vec[NSX_VEC_RESIDUAL].p, c.n);
+  });
+}
+
 int nsx_assemble_cells(nsx_ctx *ctx, int mode, double nu, double dt, double p_out) {
   return guarded(ctx, [&] {
     need_final(*ctx);

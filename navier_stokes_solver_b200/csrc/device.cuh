@@ -308,7 +308,8 @@ void spmv_probe(Ctx &c, const DevCSR &A, int what, const double *x, double *sink
 
 // ---- assemble.cu ----------------------------------------------------------------------------
 void build_assembly_maps(Ctx &c);
-void assemble_cells(Ctx &c, int mode, double nu, double dt, double p_out);
+void assemble_cells(Ctx &c, int mode, double nu, double dt, double p_out, bool res_only = false);
+void assemble_residual(Ctx &c, int mode, double nu, double dt, double p_out);
 void apply_boundary_values(Ctx &c, bool apply_inlet);
 void assemble(Ctx &c, int mode, bool apply_inlet, double nu, double dt, double p_out);
 void lift_drag(Ctx &c, double nu, double *drag, double *lift);

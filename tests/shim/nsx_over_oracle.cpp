@@ -74,6 +74,9 @@ int nsx_vec_download_ghosts(nsx_ctx *, int, double *, double *) { return NSX_OK;
 int nsx_assemble(nsx_ctx *c, int mode, int apply_inlet, double nu, double dt, double p_out, double *residual_l2) {
   return map_rc(c, orc_assemble(c->P, mode, apply_inlet, nu, dt, p_out, residual_l2));
 }
+int nsx_assemble_residual(nsx_ctx *c, int mode, double nu, double dt, double p_out, double *residual_l2) {
+  return map_rc(c, orc_assemble(c->P, mode, 0, nu, dt, p_out, residual_l2));   // the oracle has no short cut: same residual
+}
 int nsx_solve(nsx_ctx *c, int flavour, int solver, int prec, double tol, int max_it, double alpha, int *iterations, double *final_residual) {
   int64_t inner[3];
   return map_rc(c, orc_solve(c->P, flavour, solver, prec, tol, max_it, alpha, iterations, final_residual, inner));

@@ -32,7 +32,7 @@ def cpu_apps(tmp_path_factory):
 
 def history(stdout):
     newton = [float(x) for x in re.findall(r"Newton iteration \d+/\d+ - \|\|r\|\| = ([0-9.e+-]+)", stdout)]
-    krylov = [int(x) for x in re.findall(r"   (\d+) solver iterations", stdout)]
+    krylov = [int(x) for x in re.findall(r"   (\d+) (?:solver )?iterations", stdout)]
     trials = [(float(a), float(r)) for a, r in re.findall(r"Evaluating alpha=([0-9.e+-]+), \|\|r\|\|=([0-9.e+-]+)", stdout)]
     return newton, krylov, trials
 

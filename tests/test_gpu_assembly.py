@@ -119,3 +119,34 @@ def test_new_mesh_newton(tmp_path):
         block_close(dev.values(blk), orc.values(blk), f"new_mesh block {blk}")
     assert abs(r_d - r_o) <= 1e-12 * r_o
     assert dev.stat("ASSEMBLY_COLOURS") < 40
+
+
+@pytest.mark.parametrize("elem", ["quad", "tri"])
+@pytest.mark.parametrize("mode", [N.MODE_STOKES, N.MODE_NEWTON, N.MODE_UNSTEADY_FIRST, N.MODE_UNSTEADY_NEWTON])
+def test_residual_only_assembly_is_the_full_assembly_s_residual(elem, mode):
+    """nsx_assemble_residual (the line search's assembly): the residual vector, its norm and the Dirichlet entries of delta are
+    bit for bit what the full assembly with homogeneous values leaves; the matrices are not touched."""
+    d = N.Disc.generate(14, 6) if elem == "quad" else N.Disc.generate(12, 6, triangles=True)
+    dev = N.Device(d)
+    rng = np.random.default_rng(5)
+    sol, old = N.synthetic_state(d, 3), N.synthetic_state(d, 4)
+    dev.upload(N.VEC_SOLUTION, sol)
+    dev.upload(N.VEC_SOLUTION_OLD, old)
+    dev.upload(N.VEC_DELTA, rng.uniform(-1, 1, d.n))
+    r_full = dev.assemble(mode, False, 1 / 30.0, 0.01)
+    res_full, delta_full = dev.download(N.VEC_RESIDUAL), dev.download(N.VEC_DELTA)
+    mats = {b: dev.values(b) for b in (N.BLOCK_F, N.BLOCK_BT, N.BLOCK_B, N.BLOCK_MP)}
+    # another state: the residual-only call must follow the state, the matrices must stay
+    dev.upload(N.VEC_SOLUTION, sol * 1.5)
+    r_other = dev.assemble_residual(mode, 1 / 30.0, 0.01)
+    for b, v in mats.items():
+        np.testing.assert_array_equal(dev.values(b), v)
+    if mode in (N.MODE_NEWTON, N.MODE_UNSTEADY_NEWTON):
+        assert r_other != r_full
+    dev.upload(N.VEC_SOLUTION, sol)
+    dev.upload(N.VEC_DELTA, rng.uniform(-1, 1, d.n))
+    r_only = dev.assemble_residual(mode, 1 / 30.0, 0.01)
+    assert r_only == r_full
+    np.testing.assert_array_equal(dev.download(N.VEC_RESIDUAL), res_full)
+    bc = d.array("BC_DOF")
+    assert (dev.download(N.VEC_DELTA)[bc] == 0).all() and (delta_full[bc] == 0).all()
