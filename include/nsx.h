@@ -39,7 +39,9 @@ enum nsx_flavour { NSX_STATIONARY = 0, NSX_UNSTEADY = 1 }; /* which header's pre
 enum nsx_option {
   NSX_OPT_ORDERING = 0,   /* elimination order of ILU(0)/SGS: 0 natural (as Ifpack), 1 multicolour over the whole owned range,
                              2 (default) the owned range cut into spatially compact blocks (one CTA each, the structure of the
-                             reference's overlap-0 Ifpack preconditioners under mpirun -n <#blocks>), multicolour inside a block */
+                             reference's overlap-0 Ifpack preconditioners under mpirun -n <#blocks>), multicolour inside a block;
+                             3 the same blocks with Ifpack's natural (ascending index) order inside each: many more dependency
+                             levels per block, the stronger ILU(0) (what a single ILU application per iteration needs) */
   NSX_OPT_VERBOSE = 1,
   NSX_OPT_ORTHO = 2,      /* Gram-Schmidt of GMRES/FGMRES: 0 modified chain (as deal.II), 1 batched classical, two passes (default),
                              2 as 1 for the outer solver, one pass + conditional second pass for the inner FGMRES solves */

@@ -175,11 +175,13 @@ class NSSolver {
     pcout << "===============================================" << std::endl;
     compute_lift_coeff();
     pcout << "Lift coefficient: " << lift_coeff << std::endl;
+    print_more_digits(pcout, "lift coefficient", lift_coeff);
   }
   void print_drag_coeff() {
     pcout << "===============================================" << std::endl;
     compute_drag_coeff();
     pcout << "Drag coefficient: " << drag_coeff << std::endl;
+    print_more_digits(pcout, "drag coefficient", drag_coeff);
   }
 
   Problem prob;

@@ -9,6 +9,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cctype>
 #include <cerrno>
 #include <ctime>
@@ -54,6 +55,15 @@ struct Pcout {
   Pcout &operator<<(std::ostream &(*m)(std::ostream &)) { if (on) std::cout << m; return *this; }
   Pcout &operator<<(std::ios_base &(*m)(std::ios_base &)) { if (on) std::cout << m; return *this; }
 };
+
+// NSX_PRINT_DIGITS=n: after a coefficient line of the reference (6 significant digits), the same value with n digits
+template <class Out> inline void print_more_digits(Out &pcout, const char *label, double value) {
+  if (const char *e = std::getenv("NSX_PRINT_DIGITS")) {
+    char buf[96];
+    std::snprintf(buf, sizeof buf, "  [nsx] %s = %.*e", label, std::max(1, std::atoi(e)) - 1, value);
+    pcout << buf << std::endl;
+  }
+}
 
 inline void check(nsx_ctx *ctx, int rc, const char *what) {
   if (rc == NSX_OK) return;
@@ -145,6 +155,11 @@ struct Problem {
   void to_device(double inlet_amplitude) {
     int ndev_rc = nsx_create(ranks.rank, ranks.size, ranks.local_rank, nullptr, &ctx);
     if (ndev_rc != NSX_OK) throw std::runtime_error("nsx_create failed: no usable CUDA device (this build has no CPU path)");
+    // library options from the environment; unset = the library's defaults
+    const struct { const char *env; int opt; } opts[] = {{"NSX_ORDERING", NSX_OPT_ORDERING}, {"NSX_ORTHO", NSX_OPT_ORTHO}, {"NSX_BLOCK_ROWS", NSX_OPT_BLOCK_ROWS},
+                                                        {"NSX_DECOUPLE", NSX_OPT_DECOUPLE}, {"NSX_HOST_INNER", NSX_OPT_HOST_INNER}, {"NSX_VERBOSE", NSX_OPT_VERBOSE}};
+    for (const auto &o : opts)
+      if (const char *v = std::getenv(o.env)) check(ctx, nsx_set_option(ctx, o.opt, std::atoll(v)), o.env);
     const bool local = ranks.size > 1;
     const int64_t n_u = info(NSX_DI_N_U), n_p = info(NSX_DI_N_P);
     n_u_owned = local ? info(NSX_DI_N_U_OWNED) : n_u;

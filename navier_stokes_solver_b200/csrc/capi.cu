@@ -120,7 +120,7 @@ int nsx_set_option(nsx_ctx *ctx, int option, int64_t value) {
   return guarded(ctx, [&] {
     switch (option) {
       case NSX_OPT_ORDERING:
-        if (value < 0 || value > 2) throw std::invalid_argument("ordering must be 0 (natural), 1 (multicolour) or 2 (multicolour inside CTA-local blocks)");
+        if (value < 0 || value > 3) throw std::invalid_argument("ordering must be 0 (natural), 1 (multicolour), 2 (multicolour inside CTA-local blocks) or 3 (natural inside CTA-local blocks)");
         ctx->ordering = (int)value; break;
       case NSX_OPT_BLOCK_ROWS:
         if (value < 0 || value > 4096) throw std::invalid_argument("block rows must lie in [0, 4096] (0: automatic)");

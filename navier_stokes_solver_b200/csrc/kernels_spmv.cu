@@ -337,8 +337,11 @@ __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, 
     const int64_t s1 = d.a1, s2 = d.a2 - d.c1;  // stage index = global index - s
     const int nr = d.r1 - d.r0, roff = d.r0 & 1;
     if (DIRECT) {
+      // lanes per row follow the block's mean row length (host-side choice): four predicated entries per lane and trip
       if (paired) direct_rows<NSX_DL / 2, true>(S, d, two, x1, x2, yy, add, tid);
-      else direct_rows<NSX_DL, false>(S, d, two, x1, x2, yy, add, tid);
+      else if (d.lanes >= 16) direct_rows<16, false>(S, d, two, x1, x2, yy, add, tid);
+      else if (d.lanes == 8) direct_rows<8, false>(S, d, two, x1, x2, yy, add, tid);
+      else direct_rows<4, false>(S, d, two, x1, x2, yy, add, tid);
     } else {
     // phase 1: products in place (every consumer thread busy, four independent gathers each)
 #pragma unroll 4
@@ -409,7 +412,7 @@ void append_row_descs(std::vector<RowBlockDesc> &h, const DevCSR &A1, const DevC
     }
     d.r0 = (int)r0; d.r1 = (int)r1; d.kind = kind;
     const double mean = (double)(d.n1 + d.n2) / (double)(r1 - r0);
-    d.lanes = mean >= 12 ? 8 : 4;
+    d.lanes = mean > 40 ? 16 : mean > 14 ? 8 : 4;
     h.push_back(d);
     r0 = r1;
   };

@@ -356,7 +356,7 @@ __global__ void k_fg_begin(FgDev *st, const double *beta2, double tol, int max_i
 
 // One warp: the inputs are fetched in parallel into shared memory, lane 0 runs the short sequential recurrences there.
 __global__ void __launch_bounds__(32) k_fg_step(FgDev *st, const double *slots, int j, int mode, FgRec *rec, long long seq) {
-  __shared__ double col[34], cs[32], sn[32], g[34], h2s[32];
+  __shared__ double col[34], cs[32], sn[32], g[34], h2s[32], ys[32], Rs[30 * 32];
   const int lane = threadIdx.x;
   if (st->gate >= 2) { if (lane == 0) fg_publish(st, rec, seq); return; }
   // gather: coefficients of this column, the rotations so far, the rotated right-hand side
@@ -393,15 +393,18 @@ __global__ void __launch_bounds__(32) k_fg_step(FgDev *st, const double *slots, 
     verdict = fg_check(st, ++it, res);
   }
   if (verdict != 0 || j == 29) {   // y of the (j+1) x j least-squares problem: back substitution in the rotated columns
-    // lane cc keeps y[cc]; row i: y[i] = (g[i] - sum_{cc > i} R[cc][i] y[cc]) / R[i][i]
-    double ycc = 0.0;
-    for (int i = j - 1; i >= 0; --i) {
-      double t = (lane > i && lane < j) ? st->R[lane][i] * ycc : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      const double yi = (g[i] - t) / st->R[i][i];
-      if (lane == i) ycc = yi;
+    // the rotated columns come into shared memory in parallel; lane 0 substitutes back in the textbook order
+    for (int e = lane; e < j * 32; e += 32) Rs[e] = st->R[e >> 5][e & 31];
+    __syncwarp();
+    if (lane == 0) {
+      for (int i = j - 1; i >= 0; --i) {
+        double s = g[i];
+        for (int cc = i + 1; cc < j; ++cc) s -= Rs[cc * 32 + i] * ys[cc];
+        ys[i] = s / Rs[i * 32 + i];
+      }
     }
+    __syncwarp();
+    const double ycc = lane < j ? ys[lane] : 0.0;
     if (lane < j) st->y[lane] = ycc;
     __syncwarp();
     if (lane == 0) {

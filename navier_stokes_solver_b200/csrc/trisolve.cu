@@ -495,7 +495,7 @@ TriPlan &tri_plan(Ctx &c, int block, int variant) {
   // partitioned system -- belong to no group).  Ordering 2: every owned range is cut further into spatially compact
   // blocks that one CTA sweeps out of shared memory (what the reference's preconditioners are under mpirun -n <#blocks>).
   std::vector<int32_t> range(std::max<int64_t>(n, A.ncols), -1);
-  if (c.ordering == 2) {
+  if (c.ordering >= 2) {
     int ng = 0;
     for (size_t r = 0; r + 1 < owned.size(); ++r)
       if (owned[r + 1] > owned[r]) ng += geometric_blocks(c, block, A.h_rowptr, owned[r], owned[r + 1], ng, range);
@@ -509,9 +509,9 @@ TriPlan &tri_plan(Ctx &c, int block, int variant) {
   if (c.ordering == 0) {
     std::iota(perm.begin(), perm.end(), 0);
   } else {
-    std::vector<int32_t> colour(n, -1), stamp;
-    int ncol = 0;
-    for (int64_t i = 0; i < n; ++i) {
+    std::vector<int32_t> colour(n, c.ordering == 3 ? 0 : -1), stamp;   // ordering 3: one "colour", i.e. the natural order inside every block
+    int ncol = c.ordering == 3 ? 1 : 0;
+    for (int64_t i = 0; i < n && c.ordering != 3; ++i) {
       stamp.assign(ncol + 1, 0);
       for (int64_t k = A.h_rowptr[i]; k < A.h_rowptr[i + 1]; ++k) {
         const int32_t j = A.h_col[k];
