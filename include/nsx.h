@@ -48,9 +48,12 @@ enum nsx_option {
   NSX_OPT_COOP_SWEEP = 3, /* ILU/SGS sweeps: 1 colour-phased persistent kernel with its own grid barrier (default, multicolour order), 2 level-phased cooperative launch, 0 one launch per level */
   NSX_OPT_STREAM_SPMV = 4, /* SpMV kernel: 3 TMA-fed persistent, rows reduced from the stage, paired velocity columns (default); 2 TMA-fed, products staged; 1 streaming with plain loads; 0 sub-warp per row */
   NSX_OPT_BLOCK_ROWS = 5, /* ordering 2: target rows per block (0 = automatic: rows / #SMs clamped to [512, 4096]) */
-  NSX_OPT_DECOUPLE = 7,   /* 1 (default): while every coupling between the two velocity components in F is an exact zero (Stokes-type
-                             branches; checked on the device after each assembly) the inner solves' F products and the Gauss-Seidel
-                             sweeps run on the same-component entries only; 0: always the full pattern */
+  NSX_OPT_DECOUPLE = 7,   /* Exact, cheaper views of F, chosen from its current VALUES (checked on the device after each assembly):
+                             1: while every coupling between the two velocity components is an exact zero (the Stokes-type branches)
+                             the inner solves' F products and the Gauss-Seidel sweeps run on the same-component entries only;
+                             2 (default): when moreover F(u_x a, u_x b) == F(u_y a, u_y b) bit for bit, i.e. F = K (x) I_2, one scalar
+                             matrix over the velocity nodes serves both components in the SpMV and in the SGS / ILU(0) sweeps
+                             (orderings 2 and 3); 0: always the full pattern */
   NSX_OPT_HOST_INNER = 6  /* 1: the inner FGMRES solves run their recurrences on the host (one stream synchronisation per
                              iteration, round-1 behaviour); 0 (default): device-side Givens / convergence decision, the host
                              polls a mapped record and launches the next sweep speculatively */
@@ -60,7 +63,7 @@ enum nsx_stat {
   NSX_STAT_LEVELS_F = 4, NSX_STAT_LEVELS_MP = 5, NSX_STAT_LEVELS_S = 6, NSX_STAT_SPMV_CALLS = 7,
   NSX_STAT_ASSEMBLY_COLOURS = 8, NSX_STAT_ASSEMBLY_TABLES = 9, NSX_STAT_LAST_STEP = 10,
   NSX_STAT_HALO_EXCHANGES = 11, NSX_STAT_ALLREDUCES = 12,
-  NSX_STAT_F_DECOUPLED = 13 /* 1 if the last check found F's cross-component entries all zero (the decoupled view is in use) */
+  NSX_STAT_F_DECOUPLED = 13 /* view found by the last check of NSX_OPT_DECOUPLE: 0 full, 1 same-component, 2 nodes */
 };
 
 /* ctor of the solver objects (NSSolverStationary.hpp:339-351): one context per rank / GPU.
@@ -177,8 +180,8 @@ int nsx_get_ordering(nsx_ctx *ctx, int block, int32_t *perm);
 /* ordering 2: the blocks of the block-local sweeps -- block b eliminates perm[offsets[b] .. offsets[b+1]) in that order and
  * drops its couplings to other blocks; n_blocks = 0 for orderings 0 / 1.  offsets (n_blocks + 1 entries) may be NULL. */
 int nsx_get_sweep_blocks(nsx_ctx *ctx, int block, int32_t *n_blocks, int64_t *offsets);
-/* runs the check of NSX_OPT_DECOUPLE on the current values of F: *yes = 1 if Gauss-Seidel sweeps and F products of the next solve
- * will use the same-component view (NSX_BLOCK_F_DECOUPLED) */
+/* runs the check of NSX_OPT_DECOUPLE on the current values of F: *yes = the view the next solve will use (0 full matrix, 1 same-component
+ * entries, 2 velocity nodes); NSX_BLOCK_F_DECOUPLED queries that view's sweep blocks / elimination order in dof numbering */
 int nsx_check_decoupled(nsx_ctx *ctx, int *yes);
 
 #ifdef __cplusplus

@@ -435,16 +435,25 @@ class Device:
         self._ck(nsx().nsx_get_ordering(self.h, block, ptr(perm)))
         return perm
 
-    def decoupled(self):
-        """True when the current F has only exact zeros between the two velocity components: SGS sweeps and inner F products
-        then run on the same-component view (BLOCK_F_DECOUPLED)."""
+    def view(self):
+        """The exact view of F the next solve uses on the current values (NSX_OPT_DECOUPLE): 0 the full matrix, 1 same-component
+        entries only (cross-component couplings are exact zeros), 2 one scalar matrix over the velocity nodes (F = K (x) I_2)."""
         yes = C.c_int32()
         self._ck(nsx().nsx_check_decoupled(self.h, C.byref(yes)))
-        return bool(yes.value)
+        return int(yes.value)
+
+    def decoupled(self):
+        return self.view() > 0
+
+    def sweep_plan_id(self, block, ilu=False):
+        """the plan id a Gauss-Seidel (or, ilu=True, an ILU(0)) sweep on `block` uses right now: ILU(0) only follows the node view"""
+        if block != BLOCK_F:
+            return block
+        v = self.view()
+        return BLOCK_F_DECOUPLED if (v == 2 or (v == 1 and not ilu)) else block
 
     def sgs_block_id(self, block):
-        """the plan id an SGS application on `block` uses right now"""
-        return BLOCK_F_DECOUPLED if (block == BLOCK_F and self.decoupled()) else block
+        return self.sweep_plan_id(block, ilu=False)
 
     def sweep_blocks(self, block):
         """(offsets, perm) of the block-local sweeps (ordering 2): block b eliminates perm[offsets[b]:offsets[b+1]] in that order;

@@ -74,6 +74,13 @@ double *vec_of(Ctx &c, int which) {
   return c.vec[which].p;
 }
 
+// the plan behind the query id NSX_BLOCK_F_DECOUPLED: the view of F the sweeps use on the current values
+TriPlan &stokes_plan(Ctx &c) {
+  const int view = effective_view(c);
+  if (view == 0) throw std::logic_error("F couples the velocity components on its current values: there is no decoupled view");
+  return tri_plan(c, NSX_BLOCK_F, view);
+}
+
 void need_final(Ctx &c) {
   if (!c.finalized) throw std::logic_error("nsx_finalize_setup has not been called");
 }
@@ -136,7 +143,9 @@ int nsx_set_option(nsx_ctx *ctx, int option, int64_t value) {
         if (value < 0 || value > 3) throw std::invalid_argument("SpMV kernel must be 0, 1, 2 or 3");
         ctx->stream_spmv = (int)value; break;
       case NSX_OPT_HOST_INNER: ctx->host_inner = value != 0; break;
-      case NSX_OPT_DECOUPLE: ctx->decouple = value != 0; ctx->dec_epoch = 0; break;
+      case NSX_OPT_DECOUPLE:
+        if (value < 0 || value > 2) throw std::invalid_argument("decouple must be 0 (off), 1 (same-component view) or 2 (node view where it holds)");
+        ctx->decouple = value != 0; ctx->decouple_nodes = value == 2; ctx->dec_epoch = 0; break;
       default: throw std::invalid_argument("unknown option");
     }
   });
@@ -162,7 +171,7 @@ int64_t nsx_get_stat(const nsx_ctx *ctx, int stat) {
     case NSX_STAT_LAST_STEP: return ctx->last_step;
     case NSX_STAT_HALO_EXCHANGES: return ctx->stat_halo;
     case NSX_STAT_ALLREDUCES: return ctx->stat_allreduce;
-    case NSX_STAT_F_DECOUPLED: return (ctx->dec_epoch == ctx->matrix_epoch && ctx->dec_ok) ? 1 : 0;
+    case NSX_STAT_F_DECOUPLED: return (ctx->dec_epoch == ctx->matrix_epoch && ctx->dec_ok) ? (ctx->node_ok ? 2 : 1) : 0;
   }
   return -1;
 }
@@ -204,7 +213,10 @@ int nsx_set_pattern(nsx_ctx *ctx, int block, int64_t nrows, int64_t ncols, const
     set_block(c, block_ref(c, block), nrows, ncols, rowptr, col, cols_p);
     c.finalized = false;
     c.tri.erase(block);
-    if (block == NSX_BLOCK_F) { c.tri.erase(NSX_BLOCK_F + 16); c.F_cross.release(); c.Fd = DevCSR(); c.h_comp_u.clear(); c.dec_epoch = 0; }
+    if (block == NSX_BLOCK_F) {
+      c.tri.erase(NSX_BLOCK_F + 16); c.tri.erase(NSX_BLOCK_F + 32);
+      c.F_cross.release(); c.Fd = DevCSR(); c.Kn = DevCSR(); c.node_struct = 0; c.h_comp_u.clear(); c.dec_epoch = 0;
+    }
     c.matrix_epoch++;
     if (block == NSX_BLOCK_B || block == NSX_BLOCK_BT) { c.S_symbolic = false; c.tri.erase(NSX_BLOCK_S); }
   });
@@ -484,8 +496,9 @@ int nsx_inner_apply(nsx_ctx *ctx, int block, int kind, int vec_x, int vec_y) {
     const double *x = vec_of(c, vec_x);
     double *y = vec_of(c, vec_y);
     const DevCSR &A = block_ref(c, block);
-    if (kind == 0) { TriPlan &P = tri_plan(c, block, (block == NSX_BLOCK_F && decoupled_ok(c)) ? 1 : 0); tri_refresh_values(c, P, A); sgs_apply(c, P, y, x); }
-    else if (kind == 1) { TriPlan &P = tri_plan(c, block); ilu0_factor(c, P, A); ilu0_apply(c, P, y, x); }
+    const int view = block == NSX_BLOCK_F ? effective_view(c) : 0;   // the view the solvers would use on the current values
+    if (kind == 0) { TriPlan &P = tri_plan(c, block, view); tri_refresh_values(c, P, A); sgs_apply(c, P, y, x); }
+    else if (kind == 1) { TriPlan &P = tri_plan(c, block, view == 2 ? 2 : 0); ilu0_factor(c, P, A); ilu0_apply(c, P, y, x); }
     else if (kind == 2) { amg_setup(c, A); amg_apply(c, y, x); }
     else throw std::invalid_argument("inner preconditioner kind must be 0 SGS, 1 ILU(0), 2 AMG");
     NSX_CUDA(cudaStreamSynchronize(c.stream));
@@ -526,17 +539,18 @@ int nsx_precond_apply(nsx_ctx *ctx, int flavour, int prec, double alpha, int vec
 
 int nsx_get_ordering(nsx_ctx *ctx, int block, int32_t *perm) {
   return guarded(ctx, [&] {
-    TriPlan &P = block == NSX_BLOCK_F_DECOUPLED ? tri_plan(*ctx, NSX_BLOCK_F, 1) : tri_plan(*ctx, block);
-    std::copy(P.h_perm.begin(), P.h_perm.end(), perm);
+    TriPlan &P = block == NSX_BLOCK_F_DECOUPLED ? stokes_plan(*ctx) : tri_plan(*ctx, block);
+    if (P.node) for (size_t r = 0; r < P.h_perm.size(); ++r) { perm[2 * r] = 2 * P.h_perm[r]; perm[2 * r + 1] = 2 * P.h_perm[r] + 1; }   // a node = its two dofs, x first
+    else std::copy(P.h_perm.begin(), P.h_perm.end(), perm);
   });
 }
 
 int nsx_get_sweep_blocks(nsx_ctx *ctx, int block, int32_t *n_blocks, int64_t *offsets) {
   return guarded(ctx, [&] {
-    TriPlan &P = block == NSX_BLOCK_F_DECOUPLED ? tri_plan(*ctx, NSX_BLOCK_F, 1) : tri_plan(*ctx, block);
+    TriPlan &P = block == NSX_BLOCK_F_DECOUPLED ? stokes_plan(*ctx) : tri_plan(*ctx, block);
     if (!n_blocks) throw std::invalid_argument("null output pointer");
     *n_blocks = P.nblk;
-    if (offsets) std::copy(P.blk_off.begin(), P.blk_off.end(), offsets);
+    if (offsets) for (size_t b = 0; b < P.blk_off.size(); ++b) offsets[b] = P.blk_off[b] * (P.node ? 2 : 1);
   });
 }
 
@@ -544,7 +558,7 @@ int nsx_check_decoupled(nsx_ctx *ctx, int *yes) {
   return guarded(ctx, [&] {
     if (!yes) throw std::invalid_argument("null output pointer");
     need_final(*ctx);
-    *yes = decoupled_ok(*ctx) ? 1 : 0;
+    *yes = effective_view(*ctx);
   });
 }
 
@@ -563,9 +577,9 @@ int nsx_time_kernel(nsx_ctx *ctx, int what, int reps, int flush_l2, double *ms_p
     NSX_CUDA(cudaEventCreate(&e1));
     double *x = c.vec[NSX_VEC_TMP0].p, *y = c.vec[NSX_VEC_TMP1].p;
     TriPlan *P = nullptr;
-    const bool dec = (what == 1 || what == 5) && decoupled_ok(c);   // what the inner solves would run on the current values
-    if (what == 5) { P = &tri_plan(c, NSX_BLOCK_F, dec ? 1 : 0); tri_refresh_values(c, *P, c.F); }
-    if (what == 6 || what == 7) { P = &tri_plan(c, NSX_BLOCK_F); ilu0_factor(c, *P, c.F); }
+    const int view = (what == 1 || (what >= 5 && what <= 7)) ? effective_view(c) : 0;   // what the inner solves would run on the current values
+    if (what == 5) { P = &tri_plan(c, NSX_BLOCK_F, view); tri_refresh_values(c, *P, c.F); }
+    if (what == 6 || what == 7) { P = &tri_plan(c, NSX_BLOCK_F, view == 2 ? 2 : 0); ilu0_factor(c, *P, c.F); }
     double total = 0;
     const bool back_to_back = flush_l2 == 2;   // one event pair around all launches (for kernels whose input exceeds L2)
     if (back_to_back) NSX_CUDA(cudaEventRecord(e0, c.stream));
@@ -574,7 +588,7 @@ int nsx_time_kernel(nsx_ctx *ctx, int what, int reps, int flush_l2, double *ms_p
       if (!back_to_back) NSX_CUDA(cudaEventRecord(e0, c.stream));
       switch (what) {
         case 0: block_spmv(c, x, y); break;
-        case 1: spmv(c, dec ? c.Fd : c.F, x, y); break;
+        case 1: spmv(c, view == 2 ? c.Kn : view == 1 ? c.Fd : c.F, x, y); break;
         case 2: assemble_cells(c, c.time_mode, c.time_nu, c.time_dt, 1.0); break;
         case 3: vec_dot_dev(c, RED_SLOTS - 2, x, y, c.n); break;
         case 4: vec_axpy(c, y, 1e-9, x, c.n); break;

@@ -132,6 +132,7 @@ struct TriPlan {
   int64_t bl_nval = 0;
   int bl_max_rows = 0, bl_max_pass = 0, bl_ring = 0;   // sizes of the shared-memory areas (rows, passes, ring bytes)
   int bl_sgs = -1;                      // what the stream currently holds: 1 SGS values, 0 ILU factors, -1 nothing
+  bool node = false;                    // rows are velocity nodes: every row stands for the (u_x, u_y) pair of vector entries (2 row, 2 row + 1)
 };
 
 struct AmgHierarchy;  // amg.cu
@@ -193,9 +194,18 @@ struct Ctx {
   DevBuf<uint8_t> F_cross;         // per F entry: 1 = couples different components
   DevBuf<unsigned long long> cross_count;
   std::vector<uint8_t> h_comp_u;   // component of every local velocity dof (owned + ghost)
-  bool decouple = true;            // NSX_OPT_DECOUPLE
+  bool decouple = true;            // NSX_OPT_DECOUPLE (0 off, 1 same-component view only, 2 = default: node view where it holds)
+  bool decouple_nodes = true;
   long long matrix_epoch = 1, dec_epoch = 0;   // F.val changed / decision taken at
   bool dec_ok = false;
+  // Node view: when moreover F(u_x a, u_x b) == F(u_y a, u_y b) bit for bit (F = K (x) I_2, the vector Laplacian of the Stokes-type
+  // branches) one scalar matrix K over the velocity NODES serves both components: Kn holds K (columns = position of the node's
+  // x component in a vector), plan variant 2 of block F sweeps node pairs, the SpMV multiplies (x_x, x_y) pairs.
+  DevCSR Kn;
+  DevBuf<int64_t> Kn_src_x, Kn_src_y;   // Kn entry -> index of its (x,x) / (y,y) twin in F.val
+  std::vector<int64_t> h_Kn_src;
+  int node_struct = 0;             // 0 not examined, 1 the numbering pairs up, -1 it does not
+  bool node_ok = false;
   std::vector<int64_t> owned_u{0, 0}, owned_p{0, 0};
   // Dirichlet
   DevBuf<uint32_t> bc_dof;
@@ -315,7 +325,7 @@ void assemble(Ctx &c, int mode, bool apply_inlet, double nu, double dt, double p
 void lift_drag(Ctx &c, double nu, double *drag, double *lift);
 
 // ---- trisolve.cu ----------------------------------------------------------------------------
-TriPlan &tri_plan(Ctx &c, int block, int variant = 0);   // variant 1 (block F only): same-component couplings only
+TriPlan &tri_plan(Ctx &c, int block, int variant = 0);   // block F only: variant 1 same-component couplings, variant 2 velocity nodes (Ctx::Kn)
 void gather_values(Ctx &c, int64_t nnz, const int64_t *src, const double *a, double *v);   // v[k] = a[src[k]]
 void tri_refresh_values(Ctx &c, TriPlan &P, const DevCSR &A);   // permuted copy of the values
 void ilu0_factor(Ctx &c, TriPlan &P, const DevCSR &A);
@@ -326,7 +336,7 @@ DevCSR &block_ref(Ctx &c, int block);
 // ---- sweep_block.cu -------------------------------------------------------------------------
 // cuts the rows [lo, hi) of a square block into spatially compact groups (weighted recursive coordinate bisection of the
 // dof positions implied by the cell table, weights = row lengths of `rowptr`); grp[i] = first_group + k
-int geometric_blocks(Ctx &c, int block, const std::vector<int64_t> &rowptr, int64_t lo, int64_t hi, int first_group, std::vector<int32_t> &grp);
+int geometric_blocks(Ctx &c, int block, const std::vector<int64_t> &rowptr, int64_t lo, int64_t hi, int first_group, std::vector<int32_t> &grp, int stride = 1);   // stride 2: rows are velocity nodes (dof pairs)
 void bl_build(Ctx &c, TriPlan &P);                       // streams + descriptors of the block-local sweep
 void bl_refresh(Ctx &c, TriPlan &P, bool sgs);           // stream values from P.val (after tri_refresh_values / ilu0_factor)
 // y = M^-1 x.  Fused variants for the inner FGMRES: x is scaled by 1 / *scale on the way in and the scaled vector is
@@ -335,8 +345,11 @@ void bl_sweep(Ctx &c, TriPlan &P, bool sgs, double *y, const double *x, const do
 
 // ---- decouple.cu ----------------------------------------------------------------------------
 const std::vector<uint8_t> &velocity_components(Ctx &c);
-// true when every cross-component entry of F is an exact zero right now (decision cached per assembly); refreshes Fd's values
-bool decoupled_ok(Ctx &c);
+// The cheapest exact view of F on its current values (decision cached per assembly; refreshes the view's values):
+// 0 the full matrix, 1 same-component entries only (cross-component entries are all exact zeros), 2 one scalar matrix over the
+// velocity nodes (moreover the two diagonal component blocks are bit-identical)
+int stokes_view(Ctx &c);
+int effective_view(Ctx &c);   // stokes_view, limited to what the selected kernels support (node view: orderings 2 / 3 and the direct SpMV)
 
 // ---- spgemm.cu ------------------------------------------------------------------------------
 void schur_symbolic(Ctx &c);

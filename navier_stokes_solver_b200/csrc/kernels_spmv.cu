@@ -108,6 +108,7 @@ struct StreamMat {
   const double *val;
   const double *x;
   const int32_t *pcol = nullptr;  // paired columns (one even column id per two adjacent non-zeros), or null
+  int node = 0;                   // rows are velocity nodes: y(2r, 2r+1) = sum_k val_k * x(col_k, col_k + 1)
 };
 
 __device__ __forceinline__ void stream_rows(const int32_t *__restrict__ rb, int b, const StreamMat &A1, const StreamMat &A2, bool two,
@@ -279,6 +280,40 @@ __device__ __forceinline__ void direct_rows(const TmaStage &S, const RowBlockDes
   }
 }
 
+// NODE consumer: the matrix is the scalar K of F = K (x) I_2 over the velocity nodes; a column id is the position of the node's
+// x component in the vector (even, 16-byte aligned), one value multiplies the (x, y) pair, a row writes a pair.
+template <int DLX>
+__device__ __forceinline__ void direct_rows_node(const TmaStage &S, const RowBlockDesc &d, const double *__restrict__ x1, double *__restrict__ yy, int add, int tid) {
+  const double *v = S.val;
+  const int32_t *cidx = S.col;
+  const int64_t s1 = d.a1;
+  const int nr = d.r1 - d.r0, roff = d.r0 & 1;
+  const int sl = tid & (DLX - 1);
+  const unsigned hmask = DLX == 32 ? 0xffffffffu : ((1u << (DLX & 31)) - 1u) << (tid & (32 - DLX) & 31);
+  const double2 z = make_double2(0.0, 0.0);
+  for (int i = tid / DLX; i < nr; i += TCONS / DLX) {
+    const int b1 = (int)(S.rp1[roff + i] - s1), e1 = (int)(S.rp1[roff + i + 1] - s1);
+    double ax = 0, ay = 0, bx = 0, by = 0;
+    for (int k = b1 + sl; k - sl < e1; k += 4 * DLX) {
+      const bool p0 = k < e1, p1 = k + DLX < e1, p2 = k + 2 * DLX < e1, p3 = k + 3 * DLX < e1;
+      const int c0 = p0 ? cidx[k] : 0, c1 = p1 ? cidx[k + DLX] : 0, c2 = p2 ? cidx[k + 2 * DLX] : 0, c3 = p3 ? cidx[k + 3 * DLX] : 0;
+      const double2 x0 = p0 ? __ldg(reinterpret_cast<const double2 *>(x1 + c0)) : z, xb = p1 ? __ldg(reinterpret_cast<const double2 *>(x1 + c1)) : z;
+      const double2 xc = p2 ? __ldg(reinterpret_cast<const double2 *>(x1 + c2)) : z, xd = p3 ? __ldg(reinterpret_cast<const double2 *>(x1 + c3)) : z;
+      const double v0 = p0 ? v[k] : 0.0, vb = p1 ? v[k + DLX] : 0.0, vc = p2 ? v[k + 2 * DLX] : 0.0, vd = p3 ? v[k + 3 * DLX] : 0.0;
+      ax += v0 * x0.x; ay += v0 * x0.y; bx += vb * xb.x; by += vb * xb.y;
+      ax += vc * xc.x; ay += vc * xc.y; bx += vd * xd.x; by += vd * xd.y;
+    }
+    double sx = ax + bx, sy = ay + by;
+#pragma unroll
+    for (int o = DLX >> 1; o > 0; o >>= 1) { sx += __shfl_down_sync(hmask, sx, o, DLX); sy += __shfl_down_sync(hmask, sy, o, DLX); }
+    if (sl == 0) {
+      double2 *out = reinterpret_cast<double2 *>(yy) + (d.r0 + i);
+      if (add) { const double2 old = *out; sx += old.x; sy += old.y; }
+      *out = make_double2(sx, sy);
+    }
+  }
+}
+
 // Row blocks `first, first + stride, ...` of a list whose entries are of kind 0 (matrices M[0] and, if it has
 // non-zeros there, M[1] share the rows; y offset 0) or kind 1 (matrix M[2] alone; y offset yoff1).
 template <bool DIRECT>
@@ -338,7 +373,9 @@ __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, 
     const int nr = d.r1 - d.r0, roff = d.r0 & 1;
     if (DIRECT) {
       // lanes per row follow the block's mean row length (host-side choice): four predicated entries per lane and trip
-      if (paired) direct_rows<NSX_DL / 2, true>(S, d, two, x1, x2, yy, add, tid);
+      if (M[0].node) {
+        if (d.lanes >= 8) direct_rows_node<8>(S, d, x1, yy, add, tid); else direct_rows_node<4>(S, d, x1, yy, add, tid);
+      } else if (paired) direct_rows<NSX_DL / 2, true>(S, d, two, x1, x2, yy, add, tid);
       else if (d.lanes >= 16) direct_rows<16, false>(S, d, two, x1, x2, yy, add, tid);
       else if (d.lanes == 8) direct_rows<8, false>(S, d, two, x1, x2, yy, add, tid);
       else direct_rows<4, false>(S, d, two, x1, x2, yy, add, tid);
@@ -479,7 +516,7 @@ inline int pick_group(const DevCSR &A) {
 
 void spmv(Ctx &c, const DevCSR &A_, const double *x, double *y, bool add) {
   // ghost import of the input first (no-op on one GPU): a rank that owns no row of this block still has to post its sends
-  halo_exchange(c, (&A_ == &c.F || &A_ == &c.B || &A_ == &c.Fd) ? 0 : 1, x);
+  halo_exchange(c, (&A_ == &c.F || &A_ == &c.B || &A_ == &c.Fd || &A_ == &c.Kn) ? 0 : 1, x);
   if (!A_.nrows) return;
   spmv_local(c, A_, x, y, add);
 }
@@ -496,7 +533,11 @@ void spmv_local(Ctx &c, const DevCSR &A_, const double *x, double *y, bool add) 
       A.desc.upload(h, c.stream);
     }
     const int grid = std::min(A.ndesc, NSX_TMINB * c.num_sms);
-    const StreamMat M{A.rowptr.p, A.col.p, A.val.p, x, (&A_ == &c.F || &A_ == &c.B) ? pairs_for(c, A_, x) : nullptr};
+    StreamMat M{A.rowptr.p, A.col.p, A.val.p, x, (&A_ == &c.F || &A_ == &c.B) ? pairs_for(c, A_, x) : nullptr};
+    if (&A_ == &c.Kn) {
+      if (c.stream_spmv != 3 || (((uintptr_t)x | (uintptr_t)y) & 15)) throw std::logic_error("the node view of F needs the direct TMA SpMV and 16-byte aligned vectors");
+      M.node = 1;
+    }
     if (c.stream_spmv == 3) k_spmv_tma<true><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0);
     else k_spmv_tma<false><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0);
     c.stat_launches++; c.stat_spmv++;

@@ -460,24 +460,30 @@ struct Preconditioner {
   // current matrix values (NSSolverStationary.cpp:583-585, 601-604, 620-626)
   void initialize() {
     // F products of the inner solves: on the same-component entries only while the cross-component ones are exact zeros
-    const bool dec = decoupled_ok(c);
-    if (dec) opF = [this](double *y, const double *x) { spmv(c, c.Fd, x, y); };
+    // (view 1), or on the scalar matrix over the velocity nodes when moreover F = K (x) I_2 (view 2) -- decouple.cu
+    const int view = effective_view(c);
+    const bool dec = view >= 1;
+    if (view == 2) opF = [this](double *y, const double *x) { spmv(c, c.Kn, x, y); };
+    else if (dec) opF = [this](double *y, const double *x) { spmv(c, c.Fd, x, y); };
     else opF = [this](double *y, const double *x) { spmv(c, c.F, x, y); };
+    // ILU(0) of K (x) I_2 is ILU(0)(K) (x) I_2 (fill on the zero cross couplings stays zero): the node plan serves ILU too;
+    // the same-component plan (view 1) does not -- general cross positions receive fill
+    const int ilu_variant = view == 2 ? 2 : 0;
     opM = [this](double *y, const double *x) { spmv(c, c.Mp, x, y); };
     opS = [this](double *y, const double *x) { spmv(c, c.S, x, y); };
     if (type == 0) {
       // Gauss-Seidel sweeps skip exact zeros too (plan variant 1); ILU(0) needs the full pattern (fill lands on those entries)
-      F = &tri_plan(c, NSX_BLOCK_F, (flavour == NSX_STATIONARY && dec) ? 1 : 0); Mp = &tri_plan(c, NSX_BLOCK_MP);
+      F = &tri_plan(c, NSX_BLOCK_F, flavour == NSX_STATIONARY ? view : ilu_variant); Mp = &tri_plan(c, NSX_BLOCK_MP);
       if (flavour == NSX_STATIONARY) { tri_refresh_values(c, *F, c.F); tri_refresh_values(c, *Mp, c.Mp); }
       else { ilu0_factor(c, *F, c.F); ilu0_factor(c, *Mp, c.Mp); }
     } else if (type == 1) {
       Mp = &tri_plan(c, NSX_BLOCK_MP);
       if (flavour == NSX_STATIONARY) amg_setup(c, c.F);
-      else { F = &tri_plan(c, NSX_BLOCK_F); ilu0_factor(c, *F, c.F); }
+      else { F = &tri_plan(c, NSX_BLOCK_F, ilu_variant); ilu0_factor(c, *F, c.F); }
       ilu0_factor(c, *Mp, c.Mp);
     } else {
       schur_complement(c);
-      F = &tri_plan(c, NSX_BLOCK_F); S = &tri_plan(c, NSX_BLOCK_S);
+      F = &tri_plan(c, NSX_BLOCK_F, ilu_variant); S = &tri_plan(c, NSX_BLOCK_S);
       ilu0_factor(c, *F, c.F);
       ilu0_factor(c, *S, c.S);
       c.delta_p.alloc(c.nvec);

@@ -48,7 +48,8 @@ constexpr size_t SMEM_PER_CTA = (size_t)(227 * 1024 / BLOCKS_PER_SM - 1024) / 12
 //                    {T | Q << 16, rows | rounds << 16 | flags << 24, value count, index count}; flags: 1 upper sweep, 2 level ends
 struct PassHdr { int val_off, idx_off, ring16, wait; int tq, rrf, val_cnt, idx_cnt; };
 
-template <bool SGS>
+// NODE: a row is a velocity node and stands for the vector entries (2 row, 2 row + 1); one matrix value serves both components
+template <bool SGS, bool NODE>
 __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_sweep_block(const BlkDesc *__restrict__ blks, const PassHdr *__restrict__ passes, const double *__restrict__ bl_val,
                                                         const uint16_t *__restrict__ bl_idx, const int32_t *__restrict__ perm, const double *__restrict__ x,
                                                         double *__restrict__ y, const double *__restrict__ scale, double *__restrict__ v_out,
@@ -56,8 +57,9 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_sweep_block(const BlkDesc
   if (gate && *gate != 0) return;
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: ring, work vector (+ 8 zero slots for padding rows / entries), pass headers, barriers
+  constexpr int W = NODE ? 2 : 1;   // doubles per row of the work vector
   double *xs = reinterpret_cast<double *>(smem + ring_bytes);
-  PassHdr *hdr = reinterpret_cast<PassHdr *>(xs + max_rows + 8);
+  PassHdr *hdr = reinterpret_cast<PassHdr *>(xs + (size_t)W * (max_rows + 8));
   uint64_t *full = reinterpret_cast<uint64_t *>(hdr + max_pass), *empty = full + NSLOT;
   const BlkDesc B = blks[blockIdx.x];
   const int tid = threadIdx.x;
@@ -72,11 +74,17 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_sweep_block(const BlkDesc
     if (scale) { const double a = *scale; inv = isfinite(a) ? 1.0 / a : 0.0; }
     for (int i = tid; i < B.nrows; i += NT) {
       const int32_t g = perm[B.row0 + i];
-      double v = x[g];
-      if (scale) { v = inv * v; v_out[g] = v; }
-      xs[i] = v;
+      if (NODE) {
+        double2 v = reinterpret_cast<const double2 *>(x)[g];
+        if (scale) { v.x = inv * v.x; v.y = inv * v.y; reinterpret_cast<double2 *>(v_out)[g] = v; }
+        reinterpret_cast<double2 *>(xs)[i] = v;
+      } else {
+        double v = x[g];
+        if (scale) { v = inv * v; v_out[g] = v; }
+        xs[i] = v;
+      }
     }
-    if (tid < 8) xs[max_rows + tid] = 0.0;
+    if (tid < 8 * W) xs[(size_t)W * max_rows + tid] = 0.0;
   }
   __syncthreads();
   if (tid >= NC) {
@@ -106,6 +114,36 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_sweep_block(const BlkDesc
     if (tid < T) {   // warp-uniform: T is a multiple of 32
       const double *sv = reinterpret_cast<const double *>(smem + (size_t)h.ring16 * 16);
       const uint16_t *sc = reinterpret_cast<const uint16_t *>(sv + h.val_cnt);
+      const int m = sc[Q * T + tid];
+      const int behind = m & 31;
+      if (NODE) {
+        const double2 *xs2 = reinterpret_cast<const double2 *>(xs);
+        double ax = 0, ay = 0, bx = 0, by = 0;
+        int q = 0;
+        for (; q + 1 < Q; q += 2) {
+          const int i0 = q * T + tid, i1 = i0 + T;
+          const double v0 = sv[i0], v1 = sv[i1];
+          const double2 x0 = xs2[sc[i0]], x1 = xs2[sc[i1]];
+          ax = fma(v0, x0.x, ax); ay = fma(v0, x0.y, ay);
+          bx = fma(v1, x1.x, bx); by = fma(v1, x1.y, by);
+        }
+        if (q < Q) { const int i0 = q * T + tid; const double v0 = sv[i0]; const double2 x0 = xs2[sc[i0]]; ax = fma(v0, x0.x, ax); ay = fma(v0, x0.y, ay); }
+        double sx = ax + bx, sy = ay + by;
+        for (int r = 0, o = 1; r < rounds; ++r, o <<= 1) {
+          const double ux = __shfl_down_sync(0xffffffffu, sx, o), uy = __shfl_down_sync(0xffffffffu, sy, o);
+          if (o <= behind) { sx += ux; sy += uy; }
+        }
+        if (m & 0x8000) {
+          const int slot = (m >> 5) & 0x3ff;
+          const int row = sc[Q * T + T + slot];
+          const double rdiag = sv[Q * T + slot];
+          double2 r0 = xs2[row];
+          if (!(flags & 1)) { r0.x = (r0.x - sx) * rdiag; r0.y = (r0.y - sy) * rdiag; }
+          else if (SGS) { r0.x = r0.x - sx * rdiag; r0.y = r0.y - sy * rdiag; }
+          else { r0.x = (r0.x - sx) * rdiag; r0.y = (r0.y - sy) * rdiag; }
+          reinterpret_cast<double2 *>(xs)[row] = r0;
+        }
+      } else {
       double a0 = 0, a1 = 0;
       int q = 0;
       for (; q + 1 < Q; q += 2) {
@@ -117,8 +155,6 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_sweep_block(const BlkDesc
       }
       if (q < Q) { const int i0 = q * T + tid; a0 = fma(sv[i0], xs[sc[i0]], a0); }
       double s = a0 + a1;
-      const int m = sc[Q * T + tid];
-      const int behind = m & 31;
       for (int r = 0, o = 1; r < rounds; ++r, o <<= 1) {   // segmented reduction: the first lane of a row collects its lanes
         const double up = __shfl_down_sync(0xffffffffu, s, o);
         if (o <= behind) s += up;
@@ -131,12 +167,16 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_sweep_block(const BlkDesc
         if (!(flags & 1)) xs[row] = (r0 - s) * rdiag;            // w = (D + L)^-1 x   |  w = L^-1 x (rdiag = 1)
         else xs[row] = SGS ? r0 - s * rdiag : (r0 - s) * rdiag;  // y = w - D^-1 U y   |  y = U^-1 w
       }
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);   // this warp has finished reading the pass
     if (flags & 2) asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");   // the level's results are visible to the next level
   }
-  for (int i = tid; i < B.nrows; i += NC) y[perm[B.row0 + i]] = xs[i];
+  for (int i = tid; i < B.nrows; i += NC) {
+    if (NODE) reinterpret_cast<double2 *>(y)[perm[B.row0 + i]] = reinterpret_cast<const double2 *>(xs)[i];
+    else y[perm[B.row0 + i]] = xs[i];
+  }
 }
 
 // kind (low 2 bits of the map): 0 value, 1 zero, 2 reciprocal diagonal of a lower-sweep pass, 3 of an upper-sweep pass
@@ -186,7 +226,7 @@ void rcb(std::vector<Pt> &pts, int64_t lo, int64_t hi, int parts, int first, std
 
 }  // namespace
 
-int geometric_blocks(Ctx &c, int block, const std::vector<int64_t> &rowptr, int64_t lo, int64_t hi, int first_group, std::vector<int32_t> &grp) {
+int geometric_blocks(Ctx &c, int block, const std::vector<int64_t> &rowptr, int64_t lo, int64_t hi, int first_group, std::vector<int32_t> &grp, int stride) {
   const int64_t n = hi - lo;
   const bool pressure = block != NSX_BLOCK_F;
   const int64_t off = pressure ? c.n_u + c.n_ug : 0;           // position of the block's dofs in the cell table's numbering
@@ -200,8 +240,10 @@ int geometric_blocks(Ctx &c, int block, const std::vector<int64_t> &rowptr, int6
     for (int v = 0; v < nv; ++v) { cx += c.h_cell_vertices[((size_t)cell * nv + v) * 2]; cy += c.h_cell_vertices[((size_t)cell * nv + v) * 2 + 1]; }
     cx /= nv; cy /= nv;
     for (int k = 0; k < nd; ++k) {
-      const int64_t d = (int64_t)c.h_cell_dofs[(size_t)cell * nd + k] - off;
-      if (d < 0 || d >= nloc || d < lo || d >= hi) continue;
+      int64_t d = (int64_t)c.h_cell_dofs[(size_t)cell * nd + k] - off;
+      if (d < 0 || d >= nloc || (stride == 2 && (d & 1))) continue;   // node rows take the position of their x component
+      d /= stride;
+      if (d < lo || d >= hi) continue;
       sx[d - lo] += cx; sy[d - lo] += cy; cnt[d - lo]++;
     }
   }
@@ -225,8 +267,8 @@ int geometric_blocks(Ctx &c, int block, const std::vector<int64_t> &rowptr, int6
   return (int)parts;
 }
 
-static size_t bl_fixed_smem(int max_rows, int max_pass) {
-  return (size_t)(max_rows + 8) * 8 + (size_t)max_pass * sizeof(PassHdr) + 2 * NSLOT * 8;
+static size_t bl_fixed_smem(int max_rows, int max_pass, bool node) {
+  return (size_t)(max_rows + 8) * 8 * (node ? 2 : 1) + (size_t)max_pass * sizeof(PassHdr) + 2 * NSLOT * 8;
 }
 
 void bl_build(Ctx &c, TriPlan &P) {
@@ -352,7 +394,7 @@ void bl_build(Ctx &c, TriPlan &P) {
   }
   // ring schedule: every pass gets a fixed region of the shared-memory ring and the number of the pass whose consumption
   // frees it (passes are consumed in order), so the producer warp needs no bookkeeping
-  const size_t fixed = bl_fixed_smem(max_rows, max_pass);
+  const size_t fixed = bl_fixed_smem(max_rows, max_pass, P.node);
   if (fixed + 2 * (size_t)PASS_BYTES_MAX > SMEM_PER_CTA) throw std::runtime_error("block-local sweep: shared memory budget exceeded");
   const int ring_bytes = (int)((SMEM_PER_CTA - fixed) / 128 * 128);
 #pragma omp parallel for schedule(dynamic, 1)
@@ -416,19 +458,19 @@ void bl_refresh(Ctx &c, TriPlan &P, bool sgs) {
 void bl_sweep(Ctx &c, TriPlan &P, bool sgs, double *y, const double *x, const double *scale, double *v_out, const int *gate) {
   if (P.bl_sgs != (sgs ? 1 : 0)) throw std::logic_error("block-local sweep: the stream does not hold the values of this preconditioner");
   if (!P.nblk || !P.n) return;
-  const size_t smem = (size_t)P.bl_ring + bl_fixed_smem(P.bl_max_rows, P.bl_max_pass);
+  const size_t smem = (size_t)P.bl_ring + bl_fixed_smem(P.bl_max_rows, P.bl_max_pass, P.node);
+  if (P.node && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)v_out) & 15)) throw std::logic_error("block-local sweep on velocity nodes needs 16-byte aligned vectors");
+  typedef void (*Kernel)(const BlkDesc *, const PassHdr *, const double *, const uint16_t *, const int32_t *, const double *, double *, const double *, double *, const int *, int, int, int);
+  const int which = (sgs ? 1 : 0) + (P.node ? 2 : 0);
+  const Kernel kernels[4] = {k_sweep_block<false, false>, k_sweep_block<true, false>, k_sweep_block<false, true>, k_sweep_block<true, true>};
   static std::map<std::pair<int, int>, size_t> attr;   // (device, kernel) -> limit already granted
-  size_t &lim = attr[{c.device, sgs ? 1 : 0}];
+  size_t &lim = attr[{c.device, which}];
   if (lim < smem) {
-    if (sgs) NSX_CUDA(cudaFuncSetAttribute(k_sweep_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else NSX_CUDA(cudaFuncSetAttribute(k_sweep_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NSX_CUDA(cudaFuncSetAttribute(kernels[which], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lim = smem;
   }
   const PassHdr *ph = reinterpret_cast<const PassHdr *>(P.bl_pass.p);
-  if (sgs)
-    k_sweep_block<true><<<P.nblk, NT, smem, c.stream>>>(P.bl_blk.p, ph, P.bl_val.p, P.bl_idx.p, P.perm.p, x, y, scale, v_out, gate, P.bl_max_rows, P.bl_max_pass, P.bl_ring);
-  else
-    k_sweep_block<false><<<P.nblk, NT, smem, c.stream>>>(P.bl_blk.p, ph, P.bl_val.p, P.bl_idx.p, P.perm.p, x, y, scale, v_out, gate, P.bl_max_rows, P.bl_max_pass, P.bl_ring);
+  kernels[which]<<<P.nblk, NT, smem, c.stream>>>(P.bl_blk.p, ph, P.bl_val.p, P.bl_idx.p, P.perm.p, x, y, scale, v_out, gate, P.bl_max_rows, P.bl_max_pass, P.bl_ring);
   c.stat_launches++;
 }
 

@@ -467,7 +467,11 @@ TriPlan &tri_plan(Ctx &c, int block, int variant) {
     const std::vector<int32_t> *col;
   } V;
   V.nrows = A0.nrows; V.ncols = A0.ncols; V.rp = &A0.h_rowptr; V.col = &A0.h_col;
-  if (variant) {
+  if (variant == 2) {   // velocity nodes: the scalar matrix K of F = K (x) I_2 (decouple.cu)
+    if (c.node_struct != 1) throw std::logic_error("the node view of F is not available");
+    V.nrows = c.Kn.nrows; V.ncols = c.Kn.ncols; V.rp = &c.Kn.h_rowptr; V.col = &c.Kn.h_col;
+    V.orig = c.h_Kn_src;
+  } else if (variant) {
     const std::vector<uint8_t> &comp = velocity_components(c);
     V.own_rp.assign(A0.nrows + 1, 0);
     for (int64_t i = 0; i < A0.nrows; ++i) {
@@ -484,10 +488,12 @@ TriPlan &tri_plan(Ctx &c, int block, int variant) {
     V.rp = &V.own_rp; V.col = &V.own_col;
   }
   struct { int64_t nrows, ncols; const std::vector<int64_t> &h_rowptr; const std::vector<int32_t> &h_col; } A{V.nrows, V.ncols, *V.rp, *V.col};
-  const std::vector<int64_t> &owned = (block == NSX_BLOCK_F) ? c.owned_u : c.owned_p;
+  std::vector<int64_t> owned = (block == NSX_BLOCK_F) ? c.owned_u : c.owned_p;
+  if (variant == 2) for (int64_t &o : owned) o /= 2;
   std::unique_ptr<TriPlan> up(new TriPlan);
   TriPlan &P = *up;
   P.ordering = c.ordering;
+  P.node = variant == 2;
   const int64_t n = A.nrows;
   P.n = n;
   // group of each row: couplings between rows of different groups are dropped.  Orderings 0 / 1: the owned ranges (the
@@ -498,7 +504,7 @@ TriPlan &tri_plan(Ctx &c, int block, int variant) {
   if (c.ordering >= 2) {
     int ng = 0;
     for (size_t r = 0; r + 1 < owned.size(); ++r)
-      if (owned[r + 1] > owned[r]) ng += geometric_blocks(c, block, A.h_rowptr, owned[r], owned[r + 1], ng, range);
+      if (owned[r + 1] > owned[r]) ng += geometric_blocks(c, block, A.h_rowptr, owned[r], owned[r + 1], ng, range, variant == 2 ? 2 : 1);
     P.nblk = ng;
   } else {
     for (size_t r = 0; r + 1 < owned.size(); ++r)

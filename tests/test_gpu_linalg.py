@@ -218,3 +218,27 @@ def test_cooperative_sweep_equals_level_launches(setup, kind):
     finally:
         dev.set_option(N.OPT_ORDERING, 0)
         dev.set_option(N.OPT_COOP_SWEEP, 1)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_node_view_sweeps_match_oracle(kind):
+    """Stokes branch: F = K (x) I_2.  SGS and ILU(0) then sweep velocity NODES (one matrix value for both components of a node) and
+    the F product of the inner solves reads the scalar matrix; all against the oracle on the full F, given the node order expanded
+    to dofs and the same blocks."""
+    d = N.Disc.generate(16, 8)
+    orc, dev = N.Oracle(d), N.Device(d, ordering=2, block_rows=300)
+    orc.vec(0)[:] = 0
+    dev.upload(N.VEC_SOLUTION, np.zeros(d.n))
+    orc.assemble(N.MODE_STOKES, True, 1 / 10.0)
+    dev.assemble(N.MODE_STOKES, True, 1 / 10.0)
+    dev.set_values(N.BLOCK_F, orc.values(N.BLOCK_F))
+    assert dev.view() == 2
+    off, perm = dev.sweep_blocks(N.BLOCK_F_DECOUPLED)
+    assert len(off) - 1 >= 2 and (off % 2 == 0).all() and sorted(perm.tolist()) == list(range(d.n_u))
+    assert (perm[0::2] % 2 == 0).all() and (perm[1::2] == perm[0::2] + 1).all()   # a node = its x dof followed by its y dof
+    orc.set_blocks(0, off, perm)
+    x = np.random.default_rng(12).uniform(-1, 1, d.n_u)
+    y_d, y_o = dev.inner_apply(N.BLOCK_F, kind, x), orc.inner_apply(N.BLOCK_F, kind, x)
+    assert rel(y_d, y_o) < 1e-11
+    # the F product of the inner solves through the timing hook's kernel choice is not reachable from here; the solve tests cover it
+    # (test_gpu_solve.py::test_block_local_solve_matches_oracle in the Stokes-type modes)

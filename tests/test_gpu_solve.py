@@ -78,6 +78,8 @@ BLOCK_CASES = [
     (N.UNSTEADY, 1, 0, N.MODE_UNSTEADY_NEWTON, "tri"),
     (N.UNSTEADY, 1, 1, N.MODE_UNSTEADY_NEWTON, "quad"),
     (N.UNSTEADY, 1, 2, N.MODE_UNSTEADY_NEWTON, "tri"),   # config 3: single ILU applications
+    (N.UNSTEADY, 1, 2, N.MODE_UNSTEADY_FIRST, "tri"),    # config 3, first solve of a time step: ILU(0) on the node view of F
+    (N.STATIONARY, 1, 2, N.MODE_STOKES, "quad"),         # aSIMPLE in the Stokes stage: inner FGMRES + ILU(0) on the node view
 ]
 
 
@@ -89,13 +91,13 @@ def test_block_local_solve_matches_oracle(flavour, solver, prec, mode, elem, hos
     converged increment to 1e-8."""
     d, orc, dev = make(elem, mode, 1 / 10.0, ordering=2, block_rows=256)
     dev.set_option(N.OPT_HOST_INNER, host_inner)
-    sgs_on_F = flavour == N.STATIONARY and prec == 0   # Gauss-Seidel skips exact zeros (decoupled view) when the values allow; ILU never
-    for which, block in ((0, dev.sgs_block_id(N.BLOCK_F) if sgs_on_F else N.BLOCK_F), (1, N.BLOCK_MP)):
+    sgs_on_F = flavour == N.STATIONARY and prec == 0   # Gauss-Seidel follows both decoupled views of F, ILU(0) only the node view
+    for which, block in ((0, dev.sweep_plan_id(N.BLOCK_F, ilu=not sgs_on_F)), (1, N.BLOCK_MP)):
         off, perm = dev.sweep_blocks(block)
         assert len(off) - 1 >= (2 if which == 0 else 1)
         orc.set_blocks(which, off, perm)
-    if mode == N.MODE_STOKES and sgs_on_F:
-        assert dev.decoupled()
+    if mode in (N.MODE_STOKES, N.MODE_UNSTEADY_FIRST):
+        assert dev.view() == 2   # F = K (x) I_2 in the Stokes-type branches: one scalar matrix over the velocity nodes
     tol = 1e-12
     rc_o, it_o, fr_o, inner = orc.solve(flavour, solver, prec, tol, 4000)
     rc_d, it_d, fr_d = dev.solve(flavour, solver, prec, tol, 4000)
@@ -134,13 +136,18 @@ def test_decoupled_view_changes_nothing_but_the_bytes():
     for dec in (1, 0):
         d, orc, dev = make("quad", N.MODE_STOKES, 1 / 10.0)
         dev.set_option(N.OPT_DECOUPLE, dec)
-        assert dev.decoupled() == bool(dec)
+        assert dev.view() == dec
         rc, it, fr = dev.solve(N.STATIONARY, 1, 0, 1e-12, 4000)
         assert rc == 0
         out.append((it, dev.stat("INNER_F"), dev.download(N.VEC_DELTA)))
-    print("decoupled", out[0][:2], "full", out[1][:2])
+    print("same-component view", out[0][:2], "full", out[1][:2])
     assert out[0][0] == out[1][0] and abs(out[0][1] - out[1][1]) <= 2
     assert np.linalg.norm(out[0][2] - out[1][2]) <= 1e-10 * np.linalg.norm(out[1][2])
+    # the node view needs the block-local sweeps; natural order (ordering 0) falls back to the same-component view
+    d, orc, dev = make("quad", N.MODE_STOKES, 1 / 10.0)
+    assert dev.view() == 1
+    d, orc, dev = make("quad", N.MODE_STOKES, 1 / 10.0, ordering=2, block_rows=256)
+    assert dev.view() == 2
     d, orc, dev = make("quad", N.MODE_NEWTON, 1 / 10.0)
     assert not dev.decoupled()
 
