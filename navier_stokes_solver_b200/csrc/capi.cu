@@ -128,7 +128,7 @@ int nsx_set_option(nsx_ctx *ctx, int option, int64_t value) {
     switch (option) {
       case NSX_OPT_ORDERING:
         if (value < 0 || value > 3) throw std::invalid_argument("ordering must be 0 (natural), 1 (multicolour), 2 (multicolour inside CTA-local blocks) or 3 (natural inside CTA-local blocks)");
-        ctx->ordering = (int)value; break;
+        ctx->ordering = (int)value; ctx->ordering_auto = false; break;
       case NSX_OPT_BLOCK_ROWS:
         if (value < 0 || value > 4096) throw std::invalid_argument("block rows must lie in [0, 4096] (0: automatic)");
         ctx->block_rows = (int)value; ctx->tri.clear(); break;
@@ -153,9 +153,10 @@ int nsx_set_option(nsx_ctx *ctx, int option, int64_t value) {
 
 int64_t nsx_get_stat(const nsx_ctx *ctx, int stat) {
   if (!ctx) return -1;
-  auto levels = [&](int block) -> int64_t {
-    auto it = ctx->tri.find(block);
-    return it == ctx->tri.end() ? 0 : (int64_t)it->second->lvl_f.size() - 1;
+  auto levels = [&](int block) -> int64_t {   // of the block's most recently built plan
+    int64_t l = 0;
+    for (const auto &kv : ctx->tri) if ((kv.first & 15) == block) l = (int64_t)kv.second->lvl_f.size() - 1;
+    return l;
   };
   switch (stat) {
     case NSX_STAT_INNER_F: return ctx->stat_inner_F;
@@ -212,13 +213,12 @@ int nsx_set_pattern(nsx_ctx *ctx, int block, int64_t nrows, int64_t ncols, const
     if (nrows != er || ncols != ec) throw std::invalid_argument("pattern shape does not match the block (owned rows x owned + ghost columns)");
     set_block(c, block_ref(c, block), nrows, ncols, rowptr, col, cols_p);
     c.finalized = false;
-    c.tri.erase(block);
+    tri_erase(c, block);
     if (block == NSX_BLOCK_F) {
-      c.tri.erase(NSX_BLOCK_F + 16); c.tri.erase(NSX_BLOCK_F + 32);
       c.F_cross.release(); c.Fd = DevCSR(); c.Kn = DevCSR(); c.node_struct = 0; c.h_comp_u.clear(); c.dec_epoch = 0;
     }
     c.matrix_epoch++;
-    if (block == NSX_BLOCK_B || block == NSX_BLOCK_BT) { c.S_symbolic = false; c.tri.erase(NSX_BLOCK_S); }
+    if (block == NSX_BLOCK_B || block == NSX_BLOCK_BT) { c.S_symbolic = false; tri_erase(c, NSX_BLOCK_S); }
   });
 }
 

@@ -153,6 +153,7 @@ struct Ctx {
   std::string err;
   int verbose = 0;
   int ordering = 2;      // ILU / SGS elimination order: 0 natural (Ifpack), 1 multicolour over the owned range, 2 (default) multicolour inside CTA-local blocks
+  bool ordering_auto = true;   // NSX_OPT_ORDERING never set: preconditioners that are a single ILU(0) application per iteration use ordering 3
   int block_rows = 0;    // ordering 2: target rows per block (0: n / #SMs clamped to [512, 4096])
   bool host_inner = false;  // inner FGMRES recurrences on the host (round-1 behaviour) instead of the device
   // device-driven inner FGMRES (krylov.cu): recurrence state in device memory, its verdicts mirrored in a mapped host record
@@ -294,6 +295,7 @@ void fg_begin(Ctx &c, const double *beta2, double tol, int max_it, int it0);
 // 1 = first classical pass (slots[0..j], slots[64]), asks for a second pass after heavy cancellation; 2 = that second
 // pass (adds slots[32..], norm slots[65]); 3 = two passes done up front
 void fg_step(Ctx &c, const double *slots, int j, int mode);
+bool vec_multi_axpy_norm_fg(Ctx &c, int slot_norm, const VecList &V, int k, int slot_coef, double *w, int64_t n, const double *slots, int j, int mode);
 FgRec fg_wait(Ctx &c);     // spins on the mapped record until the last fg_begin / fg_step has landed
 // v = x / *a (zero if *a is not finite), skipped when *gate != 0
 void vec_scale_to_dev(Ctx &c, double *v, const double *x, const double *a, const int *gate, int64_t n);
@@ -325,7 +327,8 @@ void assemble(Ctx &c, int mode, bool apply_inlet, double nu, double dt, double p
 void lift_drag(Ctx &c, double nu, double *drag, double *lift);
 
 // ---- trisolve.cu ----------------------------------------------------------------------------
-TriPlan &tri_plan(Ctx &c, int block, int variant = 0);   // block F only: variant 1 same-component couplings, variant 2 velocity nodes (Ctx::Kn)
+TriPlan &tri_plan(Ctx &c, int block, int variant = 0, int ordering = -1);   // ordering < 0: the context's (NSX_OPT_ORDERING)
+void tri_erase(Ctx &c, int block);   // drops every cached plan of a block   // block F only: variant 1 same-component couplings, variant 2 velocity nodes (Ctx::Kn)
 void gather_values(Ctx &c, int64_t nnz, const int64_t *src, const double *a, double *v);   // v[k] = a[src[k]]
 void tri_refresh_values(Ctx &c, TriPlan &P, const DevCSR &A);   // permuted copy of the values
 void ilu0_factor(Ctx &c, TriPlan &P, const DevCSR &A);

@@ -187,153 +187,6 @@ __global__ void __launch_bounds__(VT) k_multi_axpy_norm(VecList V, int k, const 
   }
 }
 
-// ---- wide variants for 16-byte aligned vectors: two elements per load, every vector of a chunk of 8 in flight at once --------
-// The Krylov vectors of the README size are 4.3 MB each: a pass over 1 + k of them is latency-bound unless every thread has all its
-// loads of a step in flight together.  One or two steps per thread, one reduction per chunk, 2 x #SMs CTAs of 512 threads.
-constexpr int DT = 512, KC = 8;
-
-__global__ void __launch_bounds__(DT, 2) k_multi_dot2(VecList V, int k, const double *__restrict__ w, int64_t n, double *partial, unsigned int *counter, double *result) {
-  __shared__ const double *sv[32];
-  __shared__ double sh[DT / 32][KC];
-  __shared__ bool last;
-  if (threadIdx.x < 32) sv[threadIdx.x] = V.v[threadIdx.x];
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  const int64_t n2 = n >> 1;
-  const double2 *w2 = reinterpret_cast<const double2 *>(w);
-  for (int c0 = 0; c0 < k; c0 += KC) {
-    const int kc = min(KC, k - c0);
-    double acc[KC];
-#pragma unroll
-    for (int m = 0; m < KC; ++m) acc[m] = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)DT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * DT) {
-      const double2 wv = w2[i];
-      double2 vv[KC];
-#pragma unroll
-      for (int m = 0; m < KC; ++m) vv[m] = m < kc ? reinterpret_cast<const double2 *>(sv[c0 + m])[i] : make_double2(0.0, 0.0);
-#pragma unroll
-      for (int m = 0; m < KC; ++m) acc[m] = fma(wv.y, vv[m].y, fma(wv.x, vv[m].x, acc[m]));
-    }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-      const double wl = w[n - 1];
-#pragma unroll
-      for (int m = 0; m < KC; ++m) if (m < kc) acc[m] = fma(wl, sv[c0 + m][n - 1], acc[m]);
-    }
-#pragma unroll
-    for (int m = 0; m < KC; ++m) {
-      const double r = warp_sum(acc[m]);
-      if (lane == 0) sh[wp][m] = r;
-    }
-    __syncthreads();
-    if (threadIdx.x < kc) {
-      double r = 0;
-#pragma unroll
-      for (int q = 0; q < DT / 32; ++q) r += sh[q][threadIdx.x];
-      partial[(size_t)blockIdx.x * 32 + c0 + threadIdx.x] = r;
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int t = atomicInc(counter, gridDim.x - 1);
-    last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (last) {
-    __threadfence();
-    for (int m = wp; m < k; m += DT / 32) {
-      double r = 0;
-      for (int b = lane; b < gridDim.x; b += 32) r += __ldcg(&partial[(size_t)b * 32 + m]);
-      r = warp_sum(r);
-      if (lane == 0) result[m] = r;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(DT, 2) k_multi_axpy_norm2(VecList V, int k, const double *coef, double *__restrict__ w, int64_t n, double *partial,
-                                                         unsigned int *counter, double *norm2) {
-  __shared__ const double *sv[32];
-  __shared__ double sc[32];
-  __shared__ double sh[DT / 32];
-  __shared__ bool last;
-  if (threadIdx.x < 32) { sv[threadIdx.x] = V.v[threadIdx.x]; sc[threadIdx.x] = threadIdx.x < k ? coef[threadIdx.x] : 0.0; }
-  __syncthreads();
-  const int64_t n2 = n >> 1;
-  double2 *w2 = reinterpret_cast<double2 *>(w);
-  double acc = 0;
-  for (int64_t i = blockIdx.x * (int64_t)DT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * DT) {
-    double2 wv = w2[i];
-    for (int m0 = 0; m0 < k; m0 += KC) {
-      double2 vv[KC];
-#pragma unroll
-      for (int m = 0; m < KC; ++m) vv[m] = m0 + m < k ? reinterpret_cast<const double2 *>(sv[m0 + m])[i] : make_double2(0.0, 0.0);
-#pragma unroll
-      for (int m = 0; m < KC; ++m) {   // coefficients beyond k are zero: same order of subtractions as the narrow kernel
-        const double cm = sc[(m0 + m) & 31];
-        if (m0 + m < k) { wv.x -= cm * vv[m].x; wv.y -= cm * vv[m].y; }
-      }
-    }
-    w2[i] = wv;
-    acc += wv.x * wv.x + wv.y * wv.y;
-  }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    double wl = w[n - 1];
-    for (int m = 0; m < k; ++m) wl -= sc[m] * sv[m][n - 1];
-    w[n - 1] = wl;
-    acc += wl * wl;
-  }
-  // block sum over DT threads
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0;
-#pragma unroll
-    for (int q = 0; q < DT / 32; ++q) s += sh[q];
-    partial[(size_t)blockIdx.x * 32] = s;
-    __threadfence();
-    const unsigned int t = atomicInc(counter, gridDim.x - 1);
-    last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (last) {
-    __threadfence();
-    double r = 0;
-    for (int i = threadIdx.x; i < gridDim.x; i += DT) r += __ldcg(&partial[(size_t)i * 32]);
-    r = warp_sum(r);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = r;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double s = 0;
-#pragma unroll
-      for (int q = 0; q < DT / 32; ++q) s += sh[q];
-      *norm2 = s;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(VT) k_scale_to(double *__restrict__ v, const double *__restrict__ x, const double *a, const int *gate, int64_t n) {
-  if (gate && *gate != 0) return;
-  const double av = *a;
-  const bool ok = isfinite(av);
-  const double inv = 1.0 / av;
-  for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT) v[i] = ok ? inv * x[i] : 0.0;
-}
-
-__global__ void __launch_bounds__(VT) k_multi_add(double *__restrict__ x, VecList V, const double *coef, const int *count, int64_t n) {
-  __shared__ const double *sv[32];
-  __shared__ double sc[32];
-  const int k = *count;
-  if (threadIdx.x < 32) { sv[threadIdx.x] = V.v[threadIdx.x]; sc[threadIdx.x] = threadIdx.x < k ? coef[threadIdx.x] : 0.0; }
-  __syncthreads();
-  if (k <= 0) return;
-  for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT) {
-    double xi = x[i];
-    for (int m = 0; m < k; ++m) xi += sc[m] * sv[m][i];
-    x[i] = xi;
-  }
-}
-
 __device__ __forceinline__ int fg_check(const FgDev *st, int step, double value) {  // SolverControl::check -> gate code
   if (value <= st->tol) return 2;
   if (step >= st->max_it || isnan(value)) return 3;
@@ -355,9 +208,9 @@ __global__ void k_fg_begin(FgDev *st, const double *beta2, double tol, int max_i
 }
 
 // One warp: the inputs are fetched in parallel into shared memory, lane 0 runs the short sequential recurrences there.
-__global__ void __launch_bounds__(32) k_fg_step(FgDev *st, const double *slots, int j, int mode, FgRec *rec, long long seq) {
+__device__ void fg_step_body(FgDev *st, const double *slots, int j, int mode, FgRec *rec, long long seq) {
   __shared__ double col[34], cs[32], sn[32], g[34], h2s[32], ys[32], Rs[30 * 32];
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
   if (st->gate >= 2) { if (lane == 0) fg_publish(st, rec, seq); return; }
   // gather: coefficients of this column, the rotations so far, the rotated right-hand side
   {
@@ -434,9 +287,177 @@ __global__ void __launch_bounds__(32) k_fg_step(FgDev *st, const double *slots, 
   if (lane == 0) fg_publish(st, rec, seq);
 }
 
+__global__ void __launch_bounds__(32) k_fg_step(FgDev *st, const double *slots, int j, int mode, FgRec *rec, long long seq) {
+  fg_step_body(st, slots, j, mode, rec, seq);
+}
+
+// what the last CTA of the norm kernel does for the inner FGMRES on one GPU: the step kernel's work without its launch
+struct FgFuse { FgDev *st; const double *slots; int j, mode; FgRec *rec; long long seq; };
+
+// ---- wide variants for 16-byte aligned vectors: two elements per load, every vector of a chunk of 8 in flight at once --------
+// The Krylov vectors of the README size are 4.3 MB each: a pass over 1 + k of them is latency-bound unless every thread has all its
+// loads of a step in flight together.  One or two steps per thread, one reduction per chunk, 2 x #SMs CTAs of 512 threads.
+constexpr int DT = 512, KC = 8;
+
+__global__ void __launch_bounds__(DT, 2) k_multi_dot2(VecList V, int k, const double *__restrict__ w, int64_t n, double *partial, unsigned int *counter, double *result) {
+  __shared__ const double *sv[32];
+  __shared__ double sh[DT / 32][KC];
+  __shared__ bool last;
+  if (threadIdx.x < 32) sv[threadIdx.x] = V.v[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int64_t n2 = n >> 1;
+  const double2 *w2 = reinterpret_cast<const double2 *>(w);
+  for (int c0 = 0; c0 < k; c0 += KC) {
+    const int kc = min(KC, k - c0);
+    double acc[KC];
+#pragma unroll
+    for (int m = 0; m < KC; ++m) acc[m] = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)DT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * DT) {
+      const double2 wv = w2[i];
+      double2 vv[KC];
+#pragma unroll
+      for (int m = 0; m < KC; ++m) vv[m] = m < kc ? reinterpret_cast<const double2 *>(sv[c0 + m])[i] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int m = 0; m < KC; ++m) acc[m] = fma(wv.y, vv[m].y, fma(wv.x, vv[m].x, acc[m]));
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+      const double wl = w[n - 1];
+#pragma unroll
+      for (int m = 0; m < KC; ++m) if (m < kc) acc[m] = fma(wl, sv[c0 + m][n - 1], acc[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < KC; ++m) {
+      const double r = warp_sum(acc[m]);
+      if (lane == 0) sh[wp][m] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < kc) {
+      double r = 0;
+#pragma unroll
+      for (int q = 0; q < DT / 32; ++q) r += sh[q][threadIdx.x];
+      partial[(size_t)blockIdx.x * 32 + c0 + threadIdx.x] = r;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicInc(counter, gridDim.x - 1);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    for (int m = wp; m < k; m += DT / 32) {
+      double r = 0;
+      for (int b = lane; b < gridDim.x; b += 32) r += __ldcg(&partial[(size_t)b * 32 + m]);
+      r = warp_sum(r);
+      if (lane == 0) result[m] = r;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DT, 2) k_multi_axpy_norm2(VecList V, int k, const double *coef, double *__restrict__ w, int64_t n, double *partial,
+                                                         unsigned int *counter, double *norm2, FgFuse fuse) {
+  __shared__ const double *sv[32];
+  __shared__ double sc[32];
+  __shared__ double sh[DT / 32];
+  __shared__ bool last;
+  if (threadIdx.x < 32) { sv[threadIdx.x] = V.v[threadIdx.x]; sc[threadIdx.x] = threadIdx.x < k ? coef[threadIdx.x] : 0.0; }
+  __syncthreads();
+  const int64_t n2 = n >> 1;
+  double2 *w2 = reinterpret_cast<double2 *>(w);
+  double acc = 0;
+  for (int64_t i = blockIdx.x * (int64_t)DT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * DT) {
+    double2 wv = w2[i];
+    for (int m0 = 0; m0 < k; m0 += KC) {
+      double2 vv[KC];
+#pragma unroll
+      for (int m = 0; m < KC; ++m) vv[m] = m0 + m < k ? reinterpret_cast<const double2 *>(sv[m0 + m])[i] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int m = 0; m < KC; ++m) {   // coefficients beyond k are zero: same order of subtractions as the narrow kernel
+        const double cm = sc[(m0 + m) & 31];
+        if (m0 + m < k) { wv.x -= cm * vv[m].x; wv.y -= cm * vv[m].y; }
+      }
+    }
+    w2[i] = wv;
+    acc += wv.x * wv.x + wv.y * wv.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    double wl = w[n - 1];
+    for (int m = 0; m < k; ++m) wl -= sc[m] * sv[m][n - 1];
+    w[n - 1] = wl;
+    acc += wl * wl;
+  }
+  // block sum over DT threads
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+#pragma unroll
+    for (int q = 0; q < DT / 32; ++q) s += sh[q];
+    partial[(size_t)blockIdx.x * 32] = s;
+    __threadfence();
+    const unsigned int t = atomicInc(counter, gridDim.x - 1);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double r = 0;
+    for (int i = threadIdx.x; i < gridDim.x; i += DT) r += __ldcg(&partial[(size_t)i * 32]);
+    r = warp_sum(r);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0;
+#pragma unroll
+      for (int q = 0; q < DT / 32; ++q) s += sh[q];
+      *norm2 = s;
+      __threadfence();
+    }
+    if (fuse.st) {   // uniform over the grid
+      __syncthreads();
+      if (threadIdx.x < 32) fg_step_body(fuse.st, fuse.slots, fuse.j, fuse.mode, fuse.rec, fuse.seq);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(VT) k_scale_to(double *__restrict__ v, const double *__restrict__ x, const double *a, const int *gate, int64_t n) {
+  if (gate && *gate != 0) return;
+  const double av = *a;
+  const bool ok = isfinite(av);
+  const double inv = 1.0 / av;
+  for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT) v[i] = ok ? inv * x[i] : 0.0;
+}
+
+__global__ void __launch_bounds__(VT) k_multi_add(double *__restrict__ x, VecList V, const double *coef, const int *count, int64_t n) {
+  __shared__ const double *sv[32];
+  __shared__ double sc[32];
+  const int k = *count;
+  if (threadIdx.x < 32) { sv[threadIdx.x] = V.v[threadIdx.x]; sc[threadIdx.x] = threadIdx.x < k ? coef[threadIdx.x] : 0.0; }
+  __syncthreads();
+  if (k <= 0) return;
+  for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT) {
+    double xi = x[i];
+    for (int m = 0; m < k; ++m) xi += sc[m] * sv[m][i];
+    x[i] = xi;
+  }
+}
+
 }  // namespace
 
 #define LAUNCHED(c) ((c).stat_launches++)
+
+static void ensure_red(Ctx &c);
+// the wide kernels need 16-byte aligned vectors and pay off once a vector spans a few CTAs
+static bool wide_ok(const VecList &V, int k, const double *w, int64_t n) {
+  if (n < 8192 || ((uintptr_t)w & 15)) return false;
+  for (int m = 0; m < k; ++m) if ((uintptr_t)V.v[m] & 15) return false;
+  return true;
+}
+static int wide_grid(Ctx &c, int64_t n) { return grid_for(n >> 1, DT, c.num_sms * 2); }
 
 FgDev *fg_state(Ctx &c) {
   if (!c.fg_dev.p) {
@@ -456,6 +477,18 @@ void fg_step(Ctx &c, const double *slots, int j, int mode) {
   FgDev *st = fg_state(c);
   k_fg_step<<<1, 32, 0, c.stream>>>(st, slots, j, mode, (FgRec *)c.fg_rec, ++c.fg_seq); LAUNCHED(c);
 }
+// the classical pass's update + norm with the FGMRES step folded into the kernel's last CTA (one GPU, wide kernel); false if the
+// caller has to launch fg_step itself
+bool vec_multi_axpy_norm_fg(Ctx &c, int slot_norm, const VecList &V, int k, int slot_coef, double *w, int64_t n, const double *slots, int j, int mode) {
+  ensure_red(c);
+  if (c.comm || !wide_ok(V, k, w, n)) { vec_multi_axpy_norm_dev(c, slot_norm, V, k, slot_coef, w, n); return false; }
+  FgDev *st = fg_state(c);
+  k_multi_axpy_norm2<<<wide_grid(c, n), DT, 0, c.stream>>>(V, k, slot_ptr(c, slot_coef), w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot_norm),
+                                                          FgFuse{st, slots, j, mode, (FgRec *)c.fg_rec, ++c.fg_seq});
+  LAUNCHED(c);
+  return true;
+}
+
 FgRec fg_wait(Ctx &c) {
   const FgRec *rec = (const FgRec *)c.fg_rec;
   for (unsigned long long spins = 0;; ++spins) {
@@ -514,13 +547,6 @@ static void ensure_red(Ctx &c);
 
 double *slot_ptr(Ctx &c, int slot) { ensure_red(c); return c.red_result.p + slot; }
 
-// the wide kernels need 16-byte aligned vectors and pay off once a vector spans a few CTAs
-static bool wide_ok(const VecList &V, int k, const double *w, int64_t n) {
-  if (n < 8192 || ((uintptr_t)w & 15)) return false;
-  for (int m = 0; m < k; ++m) if ((uintptr_t)V.v[m] & 15) return false;
-  return true;
-}
-static int wide_grid(Ctx &c, int64_t n) { return grid_for(n >> 1, DT, c.num_sms * 2); }
 
 void vec_multi_dot_dev(Ctx &c, int slot0, const VecList &V, int k, const double *w, int64_t n) {
   ensure_red(c);
@@ -532,7 +558,7 @@ void vec_multi_dot_dev(Ctx &c, int slot0, const VecList &V, int k, const double 
 }
 void vec_multi_axpy_norm_dev(Ctx &c, int slot_norm, const VecList &V, int k, int slot_coef, double *w, int64_t n) {
   ensure_red(c);
-  if (wide_ok(V, k, w, n)) k_multi_axpy_norm2<<<wide_grid(c, n), DT, 0, c.stream>>>(V, k, slot_ptr(c, slot_coef), w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot_norm));
+  if (wide_ok(V, k, w, n)) k_multi_axpy_norm2<<<wide_grid(c, n), DT, 0, c.stream>>>(V, k, slot_ptr(c, slot_coef), w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot_norm), FgFuse{nullptr, nullptr, 0, 0, nullptr, 0});
   else k_multi_axpy_norm<<<vgrid(c, n), VT, 0, c.stream>>>(V, k, slot_ptr(c, slot_coef), w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot_norm));
   LAUNCHED(c);
   allreduce_slots(c, slot_norm, 1);

@@ -92,7 +92,7 @@ void schur_symbolic(Ctx &c) {
   c.Dvec.alloc(c.n_u);
   c.Dinv.alloc(c.n_u);
   NSX_CUDA(cudaStreamSynchronize(c.stream));
-  c.tri.erase(NSX_BLOCK_S);
+  tri_erase(c, NSX_BLOCK_S);
   c.S_symbolic = true;
 }
 

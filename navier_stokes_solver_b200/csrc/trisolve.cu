@@ -449,11 +449,12 @@ DevCSR &block_ref(Ctx &c, int block) {
   throw std::invalid_argument("unknown block id");
 }
 
-TriPlan &tri_plan(Ctx &c, int block, int variant) {
+TriPlan &tri_plan(Ctx &c, int block, int variant, int ordering) {
   if (variant && block != NSX_BLOCK_F) throw std::invalid_argument("only block F has a component-decoupled plan");
-  const int key = block + 16 * variant;
+  const int ord = ordering < 0 ? c.ordering : ordering;
+  const int key = block + 16 * variant + 256 * ord;
   auto it = c.tri.find(key);
-  if (it != c.tri.end() && it->second->ordering == c.ordering) return *it->second;
+  if (it != c.tri.end()) return *it->second;
   const DevCSR &A0 = block_ref(c, block);
   if (A0.nrows > A0.ncols) throw std::invalid_argument("triangular plan needs a square block (owned rows x owned + ghost columns on a partitioned system)");
   if (A0.h_rowptr.empty()) throw std::logic_error("block pattern is not set");
@@ -492,7 +493,7 @@ TriPlan &tri_plan(Ctx &c, int block, int variant) {
   if (variant == 2) for (int64_t &o : owned) o /= 2;
   std::unique_ptr<TriPlan> up(new TriPlan);
   TriPlan &P = *up;
-  P.ordering = c.ordering;
+  P.ordering = ord;
   P.node = variant == 2;
   const int64_t n = A.nrows;
   P.n = n;
@@ -501,7 +502,7 @@ TriPlan &tri_plan(Ctx &c, int block, int variant) {
   // partitioned system -- belong to no group).  Ordering 2: every owned range is cut further into spatially compact
   // blocks that one CTA sweeps out of shared memory (what the reference's preconditioners are under mpirun -n <#blocks>).
   std::vector<int32_t> range(std::max<int64_t>(n, A.ncols), -1);
-  if (c.ordering >= 2) {
+  if (ord >= 2) {
     int ng = 0;
     for (size_t r = 0; r + 1 < owned.size(); ++r)
       if (owned[r + 1] > owned[r]) ng += geometric_blocks(c, block, A.h_rowptr, owned[r], owned[r + 1], ng, range, variant == 2 ? 2 : 1);
@@ -512,12 +513,12 @@ TriPlan &tri_plan(Ctx &c, int block, int variant) {
   }
   // elimination order
   std::vector<int32_t> perm(n), iperm(n);
-  if (c.ordering == 0) {
+  if (ord == 0) {
     std::iota(perm.begin(), perm.end(), 0);
   } else {
-    std::vector<int32_t> colour(n, c.ordering == 3 ? 0 : -1), stamp;   // ordering 3: one "colour", i.e. the natural order inside every block
-    int ncol = c.ordering == 3 ? 1 : 0;
-    for (int64_t i = 0; i < n && c.ordering != 3; ++i) {
+    std::vector<int32_t> colour(n, ord == 3 ? 0 : -1), stamp;   // ordering 3: one "colour", i.e. the natural order inside every block
+    int ncol = ord == 3 ? 1 : 0;
+    for (int64_t i = 0; i < n && ord != 3; ++i) {
       stamp.assign(ncol + 1, 0);
       for (int64_t k = A.h_rowptr[i]; k < A.h_rowptr[i + 1]; ++k) {
         const int32_t j = A.h_col[k];
@@ -548,7 +549,7 @@ TriPlan &tri_plan(Ctx &c, int block, int variant) {
       }
       level[r] = m; nlev = std::max(nlev, m + 1);
     }
-    if (c.ordering == 1) {
+    if (ord == 1) {
       std::vector<int64_t> lp(nlev + 1, 0);
       for (int64_t r = 0; r < n; ++r) lp[level[r] + 1]++;
       for (int q = 0; q < nlev; ++q) lp[q + 1] += lp[q];
@@ -640,6 +641,11 @@ TriPlan &tri_plan(Ctx &c, int block, int variant) {
   NSX_CUDA(cudaStreamSynchronize(c.stream));
   c.tri[key] = std::move(up);
   return *c.tri[key];
+}
+
+void tri_erase(Ctx &c, int block) {
+  for (auto it = c.tri.begin(); it != c.tri.end();)
+    if ((it->first & 15) == block) it = c.tri.erase(it); else ++it;
 }
 
 void gather_values(Ctx &c, int64_t nnz, const int64_t *src, const double *a, double *v) {

@@ -173,8 +173,9 @@ def test_config2_file_mesh_block_triangular(tmp_path):
     its_orc = [int(row[1]) for row in log if row[0] == 2]
     print("Krylov iterations app   ", its_app)
     print("Krylov iterations oracle", its_orc)
-    assert len(its_app) == len(its_orc) and its_app[0] > 0 and all(i == 0 for i in its_app[1:]) and all(i == 0 for i in its_orc[1:])
-    assert abs(its_app[0] - its_orc[0]) <= max(3, 0.15 * its_orc[0])
+    # two real solves (the warm start of the second one is the first increment), then the zero-iteration breaks of the inlet ladder
+    assert len(its_app) == len(its_orc) and its_app[0] > 0 and its_app[-1] == 0 and its_orc[-1] == 0
+    assert all(abs(a - b) <= max(3, 0.15 * b) for a, b in zip(its_app, its_orc))
     drag_o, lift_o = o.lift_drag(nu)
     U_avg = 2 * (4 * u * 0.205 * (0.41 - 0.205) / 0.41 ** 2) / 3
     cl_o, cd_o = 2 * lift_o / (U_avg ** 2 * 0.1), 2 * drag_o / (U_avg ** 2 * 0.1)
