@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--solver", type=int, default=1)
     ap.add_argument("--prec", type=int, default=0)
     ap.add_argument("--tol", type=float, default=1e-10)
-    ap.add_argument("--ordering", type=int, default=2, help="ILU/SGS elimination order: 0 natural (as Ifpack), 1 multicolour over the owned range, 2 multicolour inside CTA-local blocks (library default)")
+    ap.add_argument("--ordering", type=int, default=None, help="ILU/SGS elimination order: 0 natural (as Ifpack), 1 multicolour over the owned range, 2 multicolour inside CTA-local blocks, 3 natural inside CTA-local blocks; default: the library's choice (2; 3 for the unsteady aSIMPLE)")
     ap.add_argument("--budget-s", type=float, default=780.0, help="wall-clock budget of the whole run; the step count shrinks to fit (0: off)")
     ap.add_argument("--cpu-sample-s", type=float, default=15.0, help="length of the capped CPU solve of the cpu_baseline / reference arm")
     ap.add_argument("--unsteady-mesh", default="gmsh", help="unsteady workload: 'gmsh' = the reference's new_mesh.msh (P2/P1), X,Y = generated Q3/Q2 mesh, tri:X,Y = generated P2/P1 mesh")
@@ -556,10 +556,10 @@ def main():
     if os.path.exists(tp) and world == 1:
         with open(tp) as f:
             rec = json.load(f)
-        if rec.get("mesh") == args.mesh and rec.get("ordering") == args.ordering:
+        if rec.get("mesh") == args.mesh and rec.get("ordering") == (2 if args.ordering is None else args.ordering):
             ncu_traffic = rec.get("bytes_per_launch", {})
     dom = max(share, key=share.get)
-    sweep_kernel = {0: "k_tri_level / k_tri_chain", 1: "k_sweep_phased<SGS>", 2: "k_sweep_block<SGS>"}[args.ordering]
+    sweep_kernel = {0: "k_tri_level / k_tri_chain", 1: "k_sweep_phased<SGS>", 2: "k_sweep_block<SGS>", 3: "k_sweep_block<SGS>"}[2 if args.ordering is None else args.ordering]
     dom_kernel = {"sgs_F": sweep_kernel + " (symmetric Gauss-Seidel sweeps on F, inner preconditioner of the inner FGMRES)",
                   "spmv_F": "k_spmv_tma (F SpMV of the inner FGMRES)", "block_spmv": "k_spmv_tma (Jacobian block SpMV)"}[dom]
     line = {
@@ -568,7 +568,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload_name(args, nx, ny), "cells": g.ncells, "dofs": g.n, "nnz_J_rank0": nnz_j,
                    "partition": f"{world} strips of cells, owned rows per rank (rank 0: {n} dofs)" if world > 1 else "one rank",
-                   "elimination_order": ["natural (Ifpack)", "multicolour over the owned range", f"multicolour inside {sweep_blocks} CTA-local blocks (Ifpack overlap 0 at one rank per block)"][args.ordering],
+                   "elimination_order": ["natural (Ifpack)", "multicolour over the owned range", f"multicolour inside {sweep_blocks} CTA-local blocks (Ifpack overlap 0 at one rank per block)",
+                                         f"natural inside {sweep_blocks} CTA-local blocks"][2 if args.ordering is None else args.ordering],
                    "ortho_option": args.ortho, "budget_guard": guard,
                    "outer_iterations": stats["outer"], "inner_F_iterations": stats["inner_F"], "inner_Mp_or_S_iterations": stats["inner_S"],
                    "final_residual": stats["final_res"],

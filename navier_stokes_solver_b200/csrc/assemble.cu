@@ -113,6 +113,38 @@ void build_assembly_maps(Ctx &c) {
   }
   c.color_cells.upload(cells, c.stream);
 
+  // --- partitioned system: rows of Bt for the ghost velocity dofs (for S = B diag(F)^-1 Bt, spgemm.cu), from the local cells ---
+  if (c.n_ug > 0 && c.Bt.nrows_ext == 0) {
+    DevCSR &Bt = c.Bt;
+    std::vector<std::vector<int32_t>> grow(c.n_ug);
+    for (int64_t k = 0; k < nc; ++k)
+      for (int i = 0; i < nd; ++i) {
+        if (T.dof_comp[i] == 2) continue;
+        const int64_t d = cd[k * nd + i];
+        if (d < c.n_u) continue;
+        for (int j = 0; j < nd; ++j)
+          if (T.dof_comp[j] == 2) grow[d - c.n_u].push_back((int32_t)((int64_t)cd[k * nd + j] - lu));
+      }
+    Bt.h_rowptr.resize(c.n_u + c.n_ug + 1);
+    for (int64_t g = 0; g < c.n_ug; ++g) {
+      std::sort(grow[g].begin(), grow[g].end());
+      grow[g].erase(std::unique(grow[g].begin(), grow[g].end()), grow[g].end());
+      Bt.h_rowptr[c.n_u + g + 1] = Bt.h_rowptr[c.n_u + g] + (int64_t)grow[g].size();
+      Bt.h_col.insert(Bt.h_col.end(), grow[g].begin(), grow[g].end());
+    }
+    Bt.nrows_ext = c.n_u + c.n_ug; Bt.nnz_ext = Bt.h_rowptr.back();
+    std::vector<int32_t> baked(Bt.nnz_ext);
+    for (int64_t k = 0; k < Bt.nnz_ext; ++k) baked[k] = (int32_t)(Bt.h_col[k] < c.n_p ? Bt.h_col[k] : Bt.h_col[k] + c.n_ug);
+    Bt.rowptr.alloc_padded(Bt.h_rowptr.size(), 4, c.stream);
+    NSX_CUDA(cudaMemcpyAsync(Bt.rowptr.p, Bt.h_rowptr.data(), Bt.h_rowptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
+    Bt.col.alloc_padded(Bt.nnz_ext, 16, c.stream);
+    NSX_CUDA(cudaMemcpyAsync(Bt.col.p, baked.data(), Bt.nnz_ext * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
+    Bt.val.alloc_padded(Bt.nnz_ext, 16, c.stream);
+    Bt.nrb = Bt.ndesc = 0; c.nrb_u = c.nrb_p = c.ndesc_u = c.ndesc_p = 0;
+    NSX_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  const int64_t bt_rows = c.Bt.nrows_ext ? c.Bt.nrows_ext : c.n_u;
+
   // --- row-relative offset tables, shared between cells with the same local connectivity ---
   const int tsz = nd * nd;
   std::vector<uint16_t> tables;
@@ -136,7 +168,8 @@ void build_assembly_maps(Ctx &c) {
             const bool jp = T.dof_comp[j] == 2;
             const int32_t cj = (int32_t)(jp ? (int64_t)cd[k * nd + j] - lu : cd[k * nd + j]);
             const DevCSR &A = ip ? (jp ? c.Mp : c.B) : (jp ? c.Bt : c.F);
-            t[i * nd + j] = row_owned ? (uint16_t)find_in_row(A, ri, cj) : (uint16_t)0;
+            const bool stored = row_owned || (!ip && jp && ri < bt_rows);   // ... except the ghost rows of Bt kept for the Schur product
+            t[i * nd + j] = stored ? (uint16_t)find_in_row(A, ri, cj) : (uint16_t)0;
           }
         }
       } catch (const std::exception &e) {
@@ -196,6 +229,25 @@ void build_assembly_maps(Ctx &c) {
     for (int64_t m = 0; m < c.n_p + c.n_pg; ++m) vmap[lu + m] = (int32_t)(m < c.n_p ? c.n_u + m : c.n_u + c.n_ug + m);
     c.vmap.upload(vmap, c.stream);
   }
+  // ghost velocity dofs that are Dirichlet dofs on their owner: a 0/1 mask travels through the ghost import once
+  c.n_ghost_bc = 0;
+  if (c.n_ug > 0 && c.comm) {
+    std::vector<double> mask(c.nvec, 0.0);
+    std::vector<uint32_t> bc(c.nbc);
+    if (c.nbc) NSX_CUDA(cudaMemcpyAsync(bc.data(), c.bc_dof.p, c.nbc * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+    NSX_CUDA(cudaStreamSynchronize(c.stream));
+    for (uint32_t d : bc) mask[d] = 1.0;
+    double *tmp = c.vec[NSX_VEC_TMP1].p;
+    NSX_CUDA(cudaMemcpyAsync(tmp, mask.data(), c.nvec * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    halo_exchange(c, 0, tmp);
+    NSX_CUDA(cudaMemcpyAsync(mask.data(), tmp, c.nvec * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    NSX_CUDA(cudaStreamSynchronize(c.stream));
+    std::vector<int32_t> gbc;
+    for (int64_t g = 0; g < c.n_ug; ++g) if (mask[c.n + g] != 0.0) gbc.push_back((int32_t)(c.n_u + g));
+    c.n_ghost_bc = (int64_t)gbc.size();
+    c.ghost_bc.upload(gbc, c.stream);
+    NSX_CUDA(cudaMemsetAsync(tmp, 0, c.nvec * sizeof(double), c.stream));
+  }
   c.cyl_cell.upload(c.h_cyl_cell, c.stream);
   c.cyl_face.upload(c.h_cyl_face, c.stream);
   c.face_force.alloc(2 * std::max<size_t>(1, c.h_cyl_cell.size()));
@@ -225,6 +277,7 @@ struct AsmArgs {
   const int32_t *cells;
   int ncells;
   int64_t n_u_loc, n_u_own, n_p_own;         // pressure ids of the cell table start at n_u_loc; rows >= n_*_own are ghosts
+  int64_t bt_rows;                           // rows Bt stores (the owned ones, plus the ghost rows on a partitioned system)
   int64_t F_sink, Bt_sink, B_sink, Mp_sink;  // position in each value array that swallows the ghost rows' contributions
   const int32_t *vmap;
   const FETables *fe;
@@ -289,7 +342,7 @@ __global__ void __launch_bounds__(TPC *CPB) k_assemble(const AsmArgs A) {
           sU[slot][node][comp] = s;
           sUo[slot][node][comp] = unsteady ? A.sol_old[vi] : 0.0;
           srb0[slot][i] = own ? A.F_rp[d] : A.F_sink;
-          srb1[slot][i] = own ? A.Bt_rp[d] : A.Bt_sink;
+          srb1[slot][i] = (int64_t)d < A.bt_rows ? A.Bt_rp[d] : A.Bt_sink;
         }
       }
       for (int i = lt; i < NVPC * 2; i += TPC) sxv[slot][i] = A.cell_vertices[(int64_t)cell * NVPC * 2 + i];
@@ -526,7 +579,8 @@ void assemble_cells(Ctx &c, int mode, double nu, double dt, double p_out, bool r
   A.F_val = c.F.val.p; A.Bt_val = c.Bt.val.p; A.B_val = c.B.val.p; A.Mp_val = c.Mp.val.p;
   A.cell_vertices = c.cell_vertices.p; A.cell_dofs = c.cell_dofs.p; A.cell_pat = c.cell_pat.p; A.pat_off = c.pat_off.p;
   A.n_u_loc = c.n_u + c.n_ug; A.n_u_own = c.n_u; A.n_p_own = c.n_p; A.vmap = c.vmap.p; A.fe = c.d_fe.p;
-  A.F_sink = c.F.nnz + 12; A.Bt_sink = c.Bt.nnz + 12; A.B_sink = c.B.nnz + 12; A.Mp_sink = c.Mp.nnz + 12;
+  A.bt_rows = c.Bt.nrows_ext ? c.Bt.nrows_ext : c.n_u;
+  A.F_sink = c.F.nnz + 12; A.Bt_sink = (c.Bt.nnz_ext ? c.Bt.nnz_ext : c.Bt.nnz) + 12; A.B_sink = c.B.nnz + 12; A.Mp_sink = c.Mp.nnz + 12;
   // ghost import of the state the cells read (`solution = solution_owned`, NSSolverStationary.cpp:722)
   halo_exchange(c, 0, A.sol); halo_exchange(c, 1, A.sol + c.n_u);
   if (mode >= NSX_MODE_UNSTEADY_FIRST) { halo_exchange(c, 0, A.sol_old); halo_exchange(c, 1, A.sol_old + c.n_u); }
@@ -554,7 +608,21 @@ void assemble_cells(Ctx &c, int mode, double nu, double dt, double p_out, bool r
   NSX_CUDA(cudaGetLastError());
 }
 
+namespace {
+__global__ void k_clear_rows(int64_t n, const int32_t *rows, const int64_t *rp, double *val) {
+  const int G = 8;
+  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+  if (b >= n) return;
+  const int64_t r = rows[b];
+  for (int64_t k = rp[r] + threadIdx.x % G; k < rp[r + 1]; k += G) val[k] = 0.0;
+}
+}  // namespace
+
 void apply_boundary_values(Ctx &c, bool apply_inlet) {
+  if (c.n_ghost_bc) {   // the ghost copies of constrained Bt rows follow their owners' (cleared) rows
+    k_clear_rows<<<(int)((c.n_ghost_bc * 8 + 255) / 256), 256, 0, c.stream>>>(c.n_ghost_bc, c.ghost_bc.p, c.Bt.rowptr.p, c.Bt.val.p);
+    c.stat_launches++;
+  }
   if (!c.nbc) return;
   const int nr = (int)c.owned_u.size() - 1;
   NSX_CUDA(cudaMemsetAsync(c.bc_first.p, 0xff, c.bc_first.n * sizeof(unsigned long long), c.stream));

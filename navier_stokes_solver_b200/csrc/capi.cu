@@ -49,6 +49,7 @@ void set_block(Ctx &c, DevCSR &A, int64_t nrows, int64_t ncols, const int64_t *r
   NSX_CUDA(cudaMemcpyAsync(A.col.p, dev_col, A.nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
   A.val.alloc_padded(A.nnz, 16, c.stream);  // val[nnz + 12] is the sink of the ghost rows' contributions (assemble.cu)
   A.nrb = A.ndesc = 0;
+  A.nrows_ext = A.nnz_ext = 0;
   A.pair_state = 0; A.pcol.release();
   c.nrb_u = c.nrb_p = c.ndesc_u = c.ndesc_p = 0;
   A.max_row = 0;
@@ -540,7 +541,7 @@ int nsx_precond_apply(nsx_ctx *ctx, int flavour, int prec, double alpha, int vec
 int nsx_get_ordering(nsx_ctx *ctx, int block, int32_t *perm) {
   return guarded(ctx, [&] {
     TriPlan &P = block == NSX_BLOCK_F_DECOUPLED ? stokes_plan(*ctx) : tri_plan(*ctx, block);
-    if (P.node) for (size_t r = 0; r < P.h_perm.size(); ++r) { perm[2 * r] = 2 * P.h_perm[r]; perm[2 * r + 1] = 2 * P.h_perm[r] + 1; }   // a node = its two dofs, x first
+    if (P.node) for (size_t r = 0; r < P.h_perm.size(); ++r) { perm[2 * r] = ctx->h_node_dx[P.h_perm[r]]; perm[2 * r + 1] = ctx->h_node_dy[P.h_perm[r]]; }   // a node = its two dofs, x first
     else std::copy(P.h_perm.begin(), P.h_perm.end(), perm);
   });
 }
@@ -550,7 +551,7 @@ int nsx_get_sweep_blocks(nsx_ctx *ctx, int block, int32_t *n_blocks, int64_t *of
     TriPlan &P = block == NSX_BLOCK_F_DECOUPLED ? stokes_plan(*ctx) : tri_plan(*ctx, block);
     if (!n_blocks) throw std::invalid_argument("null output pointer");
     *n_blocks = P.nblk;
-    if (offsets) for (size_t b = 0; b < P.blk_off.size(); ++b) offsets[b] = P.blk_off[b] * (P.node ? 2 : 1);
+    if (offsets) for (size_t b = 0; b < P.blk_off.size(); ++b) offsets[b] = P.blk_off[b] * (P.node ? 2 : 1);   // a node = two dofs
   });
 }
 
@@ -588,7 +589,7 @@ int nsx_time_kernel(nsx_ctx *ctx, int what, int reps, int flush_l2, double *ms_p
       if (!back_to_back) NSX_CUDA(cudaEventRecord(e0, c.stream));
       switch (what) {
         case 0: block_spmv(c, x, y); break;
-        case 1: spmv(c, view == 2 ? c.Kn : view == 1 ? c.Fd : c.F, x, y); break;
+        case 1: spmv(c, view == 2 ? c.Kn : view == 1 ? c.Fd : c.F, x, y); break;   // (Kn: the timing vectors stand for node-layout ones)
         case 2: assemble_cells(c, c.time_mode, c.time_nu, c.time_dt, 1.0); break;
         case 3: vec_dot_dev(c, RED_SLOTS - 2, x, y, c.n); break;
         case 4: vec_axpy(c, y, 1e-9, x, c.n); break;

@@ -88,52 +88,89 @@ static void build_decoupled(Ctx &c) {
   NSX_CUDA(cudaStreamSynchronize(c.stream));
 }
 
-// Structure of the node view: local velocity dofs (2a, 2a + 1) are the two components of node a, and the same-component entries
-// of rows 2a and 2a + 1 sit at columns (2b, 2b + 1) pair by pair.  True for deal.II's FESystem(FE^2) numbering; verified here.
+// Structure of the node view.  A velocity node a carries two dofs, dx(a) and dy(a) (found through the cell table: the two components
+// of a cell-local node); deal.II numbers them next to each other for vertices but component-wise inside lines and cells, so the
+// pairs are not adjacent in general.  Nodes are numbered by ascending dx.  Row dx(a) of F restricted to x columns and row dy(a)
+// restricted to y columns must hit the same nodes: then K(a, b) = F(dx a, dx b) = F(dy a, dy b) is one scalar matrix (if the values
+// agree, checked per assembly), kept as Kn with columns in the NODE LAYOUT of a vector: entry 2b = x component of node b, 2b + 1 = y.
+// One rank only for now: the node layout has no ghost import.
 static void build_node_view(Ctx &c) {
   c.node_struct = -1;
+  if (c.n_ug || c.n_pg || (c.n_u & 1)) return;
   const std::vector<uint8_t> &comp = velocity_components(c);
   const DevCSR &F = c.F;
-  const int64_t n = F.nrows, nloc = c.n_u + c.n_ug;
-  if ((n & 1) || (nloc & 1) || (c.n_ug && (c.n_p & 1))) return;   // ghost pairs must stay 16-byte aligned behind the owned pressure entries
-  for (size_t r = 0; r < c.owned_u.size(); ++r) if (c.owned_u[r] & 1) return;
-  for (int64_t d = 0; d < nloc; ++d) if (comp[d] != (d & 1)) return;
+  const int64_t n = F.nrows;
+  const FETables &T = c.fe;
+  const int nd = T.ndofs;
+  std::vector<int32_t> partner(n, -1);
+  {
+    int ldv[MAX_VN][2];
+    for (int i = 0; i < nd; ++i) if (T.dof_comp[i] < 2) ldv[T.dof_node[i]][T.dof_comp[i]] = i;
+    for (int64_t cell = 0; cell < c.ncells; ++cell)
+      for (int a = 0; a < T.nvn; ++a) {
+        const int64_t dx = c.h_cell_dofs[(size_t)cell * nd + ldv[a][0]], dy = c.h_cell_dofs[(size_t)cell * nd + ldv[a][1]];
+        if (dx >= n || dy >= n) return;
+        if ((partner[dx] >= 0 && partner[dx] != dy) || (partner[dy] >= 0 && partner[dy] != dx)) return;
+        partner[dx] = (int32_t)dy; partner[dy] = (int32_t)dx;
+      }
+  }
+  std::vector<int32_t> node_of(n, -1);
+  c.h_node_dx.clear(); c.h_node_dy.clear();
+  for (int64_t d = 0; d < n; ++d) {
+    if (partner[d] < 0) return;
+    if (comp[d] == 0) { node_of[d] = (int32_t)c.h_node_dx.size(); c.h_node_dx.push_back((int32_t)d); c.h_node_dy.push_back(partner[d]); }
+  }
+  const int64_t nn = (int64_t)c.h_node_dx.size();
+  if (2 * nn != n) return;
+  // preconditioner ranges (nsx_set_ranks) must hold whole nodes
+  c.owned_nodes.assign(c.owned_u.size(), 0);
+  for (size_t r = 0; r + 1 < c.owned_u.size(); ++r) {
+    int64_t cnt = 0;
+    for (int64_t d = c.owned_u[r]; d < c.owned_u[r + 1]; ++d) {
+      if (partner[d] < c.owned_u[r] || partner[d] >= c.owned_u[r + 1]) return;
+      cnt += comp[d] == 0;
+    }
+    c.owned_nodes[r + 1] = c.owned_nodes[r] + cnt;
+  }
   DevCSR &K = c.Kn;
-  K.nrows = n / 2; K.ncols = nloc / 2; K.row0 = 0;
-  K.h_rowptr.assign(K.nrows + 1, 0);
-  std::vector<int64_t> sx, sy;
-  std::vector<int32_t> baked;
+  K.nrows = nn; K.ncols = nn; K.row0 = 0;
+  K.h_rowptr.assign(nn + 1, 0);
   K.h_col.clear();
-  const int64_t own = c.n_u, shift = c.n_p;
+  std::vector<int64_t> sx, sy;
+  std::vector<int32_t> dev_col;
   K.max_row = 0;
-  for (int64_t a = 0; a < K.nrows; ++a) {
-    const int64_t bx = F.h_rowptr[2 * a], ex = F.h_rowptr[2 * a + 1], by = ex, ey = F.h_rowptr[2 * a + 2];
-    int64_t ky = by;
-    for (int64_t kx = bx; kx < ex; ++kx) {
+  for (int64_t a = 0; a < nn; ++a) {
+    const int64_t rx = c.h_node_dx[a], ry = c.h_node_dy[a];
+    const int32_t *yb = F.h_col.data() + F.h_rowptr[ry], *ye = F.h_col.data() + F.h_rowptr[ry + 1];
+    int64_t ny = 0;
+    for (const int32_t *q = yb; q < ye; ++q) ny += comp[*q] == 1;
+    for (int64_t kx = F.h_rowptr[rx]; kx < F.h_rowptr[rx + 1]; ++kx) {
       const int32_t cx = F.h_col[kx];
       if (comp[cx] != 0) continue;
-      while (ky < ey && comp[F.h_col[ky]] != 1) ++ky;
-      if (ky == ey || F.h_col[ky] != cx + 1) return;
-      K.h_col.push_back(cx / 2);
-      baked.push_back((int32_t)(cx < own ? cx : cx + shift));
-      sx.push_back(kx); sy.push_back(ky);
-      ++ky;
+      const int32_t cy = partner[cx];
+      const int32_t *it = std::lower_bound(yb, ye, cy);
+      if (it == ye || *it != cy) return;
+      K.h_col.push_back(node_of[cx]);
+      dev_col.push_back(2 * node_of[cx]);
+      sx.push_back(kx); sy.push_back(F.h_rowptr[ry] + (it - yb));
+      --ny;
     }
-    while (ky < ey && comp[F.h_col[ky]] != 1) ++ky;
-    if (ky != ey) return;   // the y row has a same-component entry without an x twin
+    if (ny != 0) return;   // the y row has a same-component entry without an x twin
     K.h_rowptr[a + 1] = (int64_t)K.h_col.size();
     K.max_row = std::max<int>(K.max_row, (int)(K.h_rowptr[a + 1] - K.h_rowptr[a]));
   }
-  K.nnz = K.h_rowptr[K.nrows];
+  K.nnz = K.h_rowptr[nn];
   K.rowptr.alloc_padded(K.h_rowptr.size(), 4, c.stream);
   NSX_CUDA(cudaMemcpyAsync(K.rowptr.p, K.h_rowptr.data(), K.h_rowptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
   K.col.alloc_padded(K.nnz, 16, c.stream);
-  NSX_CUDA(cudaMemcpyAsync(K.col.p, baked.data(), K.nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
+  NSX_CUDA(cudaMemcpyAsync(K.col.p, dev_col.data(), K.nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
   K.val.alloc_padded(K.nnz, 16, c.stream);
   K.nrb = K.ndesc = 0; K.pair_state = -1;
   c.Kn_src_x.upload(sx, c.stream);
   c.Kn_src_y.upload(sy, c.stream);
   c.h_Kn_src = sx;
+  c.node_dx.upload(c.h_node_dx, c.stream);
+  c.node_dy.upload(c.h_node_dy, c.stream);
   NSX_CUDA(cudaStreamSynchronize(c.stream));
   c.node_struct = 1;
 }
@@ -175,6 +212,29 @@ int stokes_view(Ctx &c) {
   if (c.node_ok) gather_values(c, c.Kn.nnz, c.Kn_src_x.p, c.F.val.p, c.Kn.val.p);
   if (c.dec_ok) gather_values(c, c.Fd.nnz, c.Fd_src.p, c.F.val.p, c.Fd.val.p);
   return c.dec_ok ? (c.node_ok ? 2 : 1) : 0;
+}
+
+namespace {
+__global__ void k_to_node_layout(int64_t nn, const int32_t *__restrict__ dx, const int32_t *__restrict__ dy, const double *__restrict__ ref, double2 *__restrict__ node) {
+  for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < nn; a += (int64_t)gridDim.x * blockDim.x) node[a] = make_double2(ref[dx[a]], ref[dy[a]]);
+}
+__global__ void k_from_node_layout(int64_t nn, const int32_t *__restrict__ dx, const int32_t *__restrict__ dy, const double2 *__restrict__ node, double *__restrict__ ref) {
+  for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < nn; a += (int64_t)gridDim.x * blockDim.x) {
+    const double2 v = node[a];
+    ref[dx[a]] = v.x; ref[dy[a]] = v.y;
+  }
+}
+}  // namespace
+
+void vec_to_node_layout(Ctx &c, double *node, const double *ref) {
+  const int64_t nn = c.Kn.nrows;
+  k_to_node_layout<<<grid_for(nn, 256, c.num_sms * 8), 256, 0, c.stream>>>(nn, c.node_dx.p, c.node_dy.p, ref, reinterpret_cast<double2 *>(node));
+  c.stat_launches++;
+}
+void vec_from_node_layout(Ctx &c, double *ref, const double *node) {
+  const int64_t nn = c.Kn.nrows;
+  k_from_node_layout<<<grid_for(nn, 256, c.num_sms * 8), 256, 0, c.stream>>>(nn, c.node_dx.p, c.node_dy.p, reinterpret_cast<const double2 *>(node), ref);
+  c.stat_launches++;
 }
 
 int effective_view(Ctx &c) {

@@ -74,6 +74,9 @@ struct alignas(16) RowBlockDesc { long long a1, a2; int c1, o1, n1, c2, o2, n2, 
 struct DevCSR {
   int64_t nrows = 0, ncols = 0, nnz = 0;
   int64_t row0 = 0;  // global (block-local) index of the first stored row: ranks store their owned rows only
+  // Bt on a partitioned system also keeps the rows of the GHOST velocity dofs behind the owned ones (assembled redundantly from
+  // the local cells, complete for owned pressure columns): what EpetraExt imports for B diag(F)^-1 Bt in the reference
+  int64_t nrows_ext = 0, nnz_ext = 0;   // rows / entries including that extension (0: none)
   DevBuf<int64_t> rowptr;
   DevBuf<int32_t> col;
   DevBuf<double> val;
@@ -132,7 +135,8 @@ struct TriPlan {
   int64_t bl_nval = 0;
   int bl_max_rows = 0, bl_max_pass = 0, bl_ring = 0;   // sizes of the shared-memory areas (rows, passes, ring bytes)
   int bl_sgs = -1;                      // what the stream currently holds: 1 SGS values, 0 ILU factors, -1 nothing
-  bool node = false;                    // rows are velocity nodes: every row stands for the (u_x, u_y) pair of vector entries (2 row, 2 row + 1)
+  bool node = false;                    // rows are velocity nodes: every row stands for the (u_x, u_y) pair of a node
+  DevBuf<int32_t> px_ref, py_ref, px_node, py_node;   // vector entries of the pair of permuted row r: reference layout / node layout
 };
 
 struct AmgHierarchy;  // amg.cu
@@ -199,12 +203,17 @@ struct Ctx {
   bool decouple_nodes = true;
   long long matrix_epoch = 1, dec_epoch = 0;   // F.val changed / decision taken at
   bool dec_ok = false;
-  // Node view: when moreover F(u_x a, u_x b) == F(u_y a, u_y b) bit for bit (F = K (x) I_2, the vector Laplacian of the Stokes-type
-  // branches) one scalar matrix K over the velocity NODES serves both components: Kn holds K (columns = position of the node's
-  // x component in a vector), plan variant 2 of block F sweeps node pairs, the SpMV multiplies (x_x, x_y) pairs.
+  // Node view: when moreover F(dx a, dx b) == F(dy a, dy b) bit for bit (F = K (x) I_2, the vector Laplacian of the Stokes-type
+  // branches) one scalar matrix K over the velocity NODES serves both components: Kn holds K with columns in the node layout of a
+  // vector (entry 2b / 2b + 1 = x / y component of node b), plan variant 2 of block F sweeps node pairs, the inner FGMRES on F runs
+  // in the node layout (its SpMV multiplies (x, y) pairs with one matrix value) and permutes only its right-hand side and result.
   DevCSR Kn;
   DevBuf<int64_t> Kn_src_x, Kn_src_y;   // Kn entry -> index of its (x,x) / (y,y) twin in F.val
   std::vector<int64_t> h_Kn_src;
+  std::vector<int32_t> h_node_dx, h_node_dy;   // the two dofs of every velocity node (nodes numbered by ascending x dof)
+  DevBuf<int32_t> node_dx, node_dy;
+  std::vector<int64_t> owned_nodes;            // owned_u in nodes
+  DevBuf<double> node_b, node_x;               // right-hand side / iterate of an inner solve in the node layout
   int node_struct = 0;             // 0 not examined, 1 the numbering pairs up, -1 it does not
   bool node_ok = false;
   std::vector<int64_t> owned_u{0, 0}, owned_p{0, 0};
@@ -242,7 +251,9 @@ struct Ctx {
   std::map<int, std::unique_ptr<TriPlan>> tri;
   std::shared_ptr<AmgHierarchy> amg;  // shared_ptr: deleter bound where the type is complete (amg.cu)
   // aSIMPLE
-  DevBuf<double> Dvec, Dinv, delta_p, tmp_u, tmp_p;
+  DevBuf<double> Dvec, Dinv, delta_p, tmp_u, tmp_p, tmp_s;
+  DevBuf<int32_t> ghost_bc;       // ghost velocity dofs that are Dirichlet dofs on their owner (their Bt rows are cleared too)
+  int64_t n_ghost_bc = 0;
   bool S_symbolic = false;
   // Krylov workspaces (outer block vectors, inner velocity / pressure vectors)
   std::vector<DevBuf<double>> work_outer, work_inner_u, work_inner_p;
@@ -339,12 +350,15 @@ DevCSR &block_ref(Ctx &c, int block);
 // ---- sweep_block.cu -------------------------------------------------------------------------
 // cuts the rows [lo, hi) of a square block into spatially compact groups (weighted recursive coordinate bisection of the
 // dof positions implied by the cell table, weights = row lengths of `rowptr`); grp[i] = first_group + k
-int geometric_blocks(Ctx &c, int block, const std::vector<int64_t> &rowptr, int64_t lo, int64_t hi, int first_group, std::vector<int32_t> &grp, int stride = 1);   // stride 2: rows are velocity nodes (dof pairs)
+int geometric_blocks(Ctx &c, int block, const std::vector<int64_t> &rowptr, int64_t lo, int64_t hi, int first_group, std::vector<int32_t> &grp,
+                     const std::vector<int32_t> *row_dof = nullptr);   // row_dof: rows are velocity nodes, row i sits where dof (*row_dof)[i] does
 void bl_build(Ctx &c, TriPlan &P);                       // streams + descriptors of the block-local sweep
 void bl_refresh(Ctx &c, TriPlan &P, bool sgs);           // stream values from P.val (after tri_refresh_values / ilu0_factor)
 // y = M^-1 x.  Fused variants for the inner FGMRES: x is scaled by 1 / *scale on the way in and the scaled vector is
 // also stored to v_out; the launch does nothing when *gate != 0 (speculative launch behind a device-side decision).
-void bl_sweep(Ctx &c, TriPlan &P, bool sgs, double *y, const double *x, const double *scale = nullptr, double *v_out = nullptr, const int *gate = nullptr);
+// A node plan reads / writes vectors in the reference layout (entries dx(a), dy(a)) or, node_layout = true, in the node layout.
+void bl_sweep(Ctx &c, TriPlan &P, bool sgs, double *y, const double *x, const double *scale = nullptr, double *v_out = nullptr, const int *gate = nullptr,
+              bool node_layout = false);
 
 // ---- decouple.cu ----------------------------------------------------------------------------
 const std::vector<uint8_t> &velocity_components(Ctx &c);
@@ -352,7 +366,9 @@ const std::vector<uint8_t> &velocity_components(Ctx &c);
 // 0 the full matrix, 1 same-component entries only (cross-component entries are all exact zeros), 2 one scalar matrix over the
 // velocity nodes (moreover the two diagonal component blocks are bit-identical)
 int stokes_view(Ctx &c);
-int effective_view(Ctx &c);   // stokes_view, limited to what the selected kernels support (node view: orderings 2 / 3 and the direct SpMV)
+int effective_view(Ctx &c);
+void vec_to_node_layout(Ctx &c, double *node, const double *ref);     // node[2a], node[2a+1] = ref[dx(a)], ref[dy(a)]
+void vec_from_node_layout(Ctx &c, double *ref, const double *node);   // stokes_view, limited to what the selected kernels support (node view: orderings 2 / 3 and the direct SpMV)
 
 // ---- spgemm.cu ------------------------------------------------------------------------------
 void schur_symbolic(Ctx &c);

@@ -280,8 +280,8 @@ __device__ __forceinline__ void direct_rows(const TmaStage &S, const RowBlockDes
   }
 }
 
-// NODE consumer: the matrix is the scalar K of F = K (x) I_2 over the velocity nodes; a column id is the position of the node's
-// x component in the vector (even, 16-byte aligned), one value multiplies the (x, y) pair, a row writes a pair.
+// NODE consumer: the matrix is the scalar K of F = K (x) I_2 over the velocity nodes, vectors are in the node layout (entry 2b / 2b + 1
+// = x / y component of node b): a column id is 2b (16-byte aligned), one value multiplies the (x, y) pair, a row writes a pair.
 template <int DLX>
 __device__ __forceinline__ void direct_rows_node(const TmaStage &S, const RowBlockDesc &d, const double *__restrict__ x1, double *__restrict__ yy, int add, int tid) {
   const double *v = S.val;

@@ -203,6 +203,7 @@ void solver_fgmres(Ctx &c, Control &ctl, const DOp &A, double *x, const double *
 struct InnerM {
   TriPlan *plan = nullptr;   // block-local SGS / ILU(0) plan, or null
   bool sgs = false;
+  bool node_layout = false;  // the solve runs on vectors in the node layout (decouple.cu)
   DOp op;                    // used when plan is null or not block-local
   bool fusable() const { return plan && plan->nblk > 0; }
 };
@@ -229,7 +230,7 @@ void solver_fgmres_dev(Ctx &c, Control &ctl, const DOp &A, double *x, const doub
   auto launch_M = [&](int j) {   // v_j = aux / a ; z_j = M^-1 v_j, both behind the device-side verdict
     if (M.fusable()) {
       if (M.sgs && M.plan->bl_sgs != 1) bl_refresh(c, *M.plan, true);
-      bl_sweep(c, *M.plan, M.sgs, z(j), aux, &st->a, v(j), &st->gate);
+      bl_sweep(c, *M.plan, M.sgs, z(j), aux, &st->a, v(j), &st->gate, M.node_layout);
     } else {
       vec_scale_to_dev(c, v(j), aux, &st->a, &st->gate, n);
       M.op(z(j), v(j));
@@ -453,7 +454,8 @@ struct Preconditioner {
   int flavour, type;
   double alpha;
   TriPlan *F = nullptr, *Mp = nullptr, *S = nullptr;
-  DOp opF, opM, opS;
+  DOp opF, opM, opS, opKn;
+  int view = 0;
 
   Preconditioner(Ctx &ctx, int fl, int ty, double al) : c(ctx), flavour(fl), type(ty), alpha(al) {}
 
@@ -462,16 +464,27 @@ struct Preconditioner {
   void initialize() {
     // F products of the inner solves: on the same-component entries only while the cross-component ones are exact zeros
     // (view 1), or on the scalar matrix over the velocity nodes when moreover F = K (x) I_2 (view 2) -- decouple.cu
-    const int view = effective_view(c);
+    view = effective_view(c);
     const bool dec = view >= 1;
-    if (view == 2) opF = [this](double *y, const double *x) { spmv(c, c.Kn, x, y); };
-    else if (dec) opF = [this](double *y, const double *x) { spmv(c, c.Fd, x, y); };
+    if (dec) opF = [this](double *y, const double *x) { spmv(c, c.Fd, x, y); };
     else opF = [this](double *y, const double *x) { spmv(c, c.F, x, y); };
+    opKn = [this](double *y, const double *x) { spmv(c, c.Kn, x, y); };   // node layout in, node layout out (view 2)
     // ILU(0) of K (x) I_2 is ILU(0)(K) (x) I_2 (fill on the zero cross couplings stays zero): the node plan serves ILU too;
     // the same-component plan (view 1) does not -- general cross positions receive fill
     const int ilu_variant = view == 2 ? 2 : 0;
     opM = [this](double *y, const double *x) { spmv(c, c.Mp, x, y); };
-    opS = [this](double *y, const double *x) { spmv(c, c.S, x, y); };
+    if (c.n_ug || c.n_pg) {
+      // partitioned: S holds the rank-local block only (what ILU(0) needs); the product is B (diag(F)^-1 (Bt x)) with the two
+      // ghost imports of the SpMVs -- the same sum as the reference's assembled S x, in another order
+      c.tmp_s.alloc(c.nvec);
+      opS = [this](double *y, const double *x) {
+        spmv(c, c.Bt, x, c.tmp_s.p);
+        vec_mul(c, c.tmp_s.p, c.Dinv.p, c.n_u);
+        spmv(c, c.B, c.tmp_s.p, y);
+      };
+    } else {
+      opS = [this](double *y, const double *x) { spmv(c, c.S, x, y); };
+    }
     if (type == 0) {
       // Gauss-Seidel sweeps skip exact zeros too (plan variant 1); ILU(0) needs the full pattern (fill lands on those entries)
       F = &tri_plan(c, NSX_BLOCK_F, flavour == NSX_STATIONARY ? view : ilu_variant); Mp = &tri_plan(c, NSX_BLOCK_MP);
@@ -503,6 +516,18 @@ struct Preconditioner {
     if (c.host_inner) { solver_fgmres(c, ctl, opF, x, b, op, W, slot0); return; }
     InnerM M;
     M.plan = plan; M.sgs = sgs; M.op = op;
+    if (view == 2 && plan && plan->node && plan->nblk) {
+      // F = K (x) I_2: the whole solve runs in the node layout -- one matrix value per node pair in the SpMV and in the sweeps --
+      // and only its right-hand side, initial guess and result are permuted
+      c.node_b.alloc(c.nvec); c.node_x.alloc(c.nvec);
+      vec_to_node_layout(c, c.node_b.p, b);
+      vec_to_node_layout(c, c.node_x.p, x);
+      M.node_layout = true;
+      try { solver_fgmres_dev(c, ctl, opKn, c.node_x.p, c.node_b.p, M, W, slot0); }
+      catch (const NoConvergence &) { vec_from_node_layout(c, x, c.node_x.p); throw; }
+      vec_from_node_layout(c, x, c.node_x.p);
+      return;
+    }
     solver_fgmres_dev(c, ctl, opF, x, b, M, W, slot0);
   }
 

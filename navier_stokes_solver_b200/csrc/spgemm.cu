@@ -13,11 +13,15 @@ namespace nsx {
 
 namespace {
 
+// n_u_own / n_p_own: owned counts.  Device columns follow the vector layout (ghost velocity ids shifted by n_p_own, ghost pressure
+// ids by the ghost velocity count): dinv is a full-layout vector, Bt's rows are indexed by the local velocity id, and only the
+// owned pressure columns are kept (S is the rank-local block: what ILU(0) factors; the product S x of the CG solve is formed
+// from B, diag(F)^-1 and Bt on a partitioned system, krylov.cu)
 __global__ void __launch_bounds__(256) k_schur(int64_t n_p, const int64_t *__restrict__ B_rp, const int32_t *__restrict__ B_col,
                                                const double *__restrict__ B_val, const double *__restrict__ dinv,
                                                const int64_t *__restrict__ Bt_rp, const int32_t *__restrict__ Bt_col,
                                                const double *__restrict__ Bt_val, const int64_t *__restrict__ S_rp,
-                                               const int32_t *__restrict__ S_col, double *__restrict__ S_val, int maxrow) {
+                                               const int32_t *__restrict__ S_col, double *__restrict__ S_val, int maxrow, int64_t n_u_own, int64_t n_p_own) {
   extern __shared__ double s_acc[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + wib;
@@ -28,10 +32,12 @@ __global__ void __launch_bounds__(256) k_schur(int64_t n_p, const int64_t *__res
   for (int t = lane; t < sl; t += 32) acc[t] = 0.0;
   __syncwarp();
   for (int64_t k = B_rp[row]; k < B_rp[row + 1]; ++k) {
-    const int32_t m = B_col[k];
-    const double a = B_val[k] * dinv[m];
+    const int32_t mb = B_col[k];
+    const double a = B_val[k] * dinv[mb];
+    const int64_t m = mb < n_u_own ? mb : mb - n_p_own;
     for (int64_t l = Bt_rp[m] + lane; l < Bt_rp[m + 1]; l += 32) {
       const int32_t cj = Bt_col[l];
+      if (cj >= n_p_own) continue;
       int lo = 0, hi = sl;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -48,8 +54,7 @@ __global__ void __launch_bounds__(256) k_schur(int64_t n_p, const int64_t *__res
 
 void schur_symbolic(Ctx &c) {
   if (c.S_symbolic) return;
-  if (c.n_ug || c.n_pg)
-    throw std::logic_error("aSIMPLE on a partitioned system needs the ghost rows of Bt (B diag(F)^-1 Bt reaches two cells deep); not built in this round");
+  if (c.n_ug && c.Bt.nrows_ext != c.n_u + c.n_ug) throw std::logic_error("the ghost rows of Bt are built by nsx_finalize_setup");
   const DevCSR &B = c.B, &Bt = c.Bt;
   DevCSR &S = c.S;
   const int64_t n = c.n_p;
@@ -62,8 +67,9 @@ void schur_symbolic(Ctx &c) {
     for (int64_t i = 0; i < n; ++i) {
       tmp.clear();
       for (int64_t k = B.h_rowptr[i]; k < B.h_rowptr[i + 1]; ++k) {
-        const int64_t m = B.h_col[k];
-        tmp.insert(tmp.end(), Bt.h_col.begin() + Bt.h_rowptr[m], Bt.h_col.begin() + Bt.h_rowptr[m + 1]);
+        const int64_t m = B.h_col[k];   // local velocity id, owned or ghost: Bt holds both kinds of rows
+        for (int64_t l = Bt.h_rowptr[m]; l < Bt.h_rowptr[m + 1]; ++l)
+          if (Bt.h_col[l] < n) tmp.push_back(Bt.h_col[l]);   // owned pressure columns: the rank-local block
       }
       std::sort(tmp.begin(), tmp.end());
       tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
@@ -89,8 +95,9 @@ void schur_symbolic(Ctx &c) {
   NSX_CUDA(cudaMemcpyAsync(S.col.p, S.h_col.data(), S.nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
   S.diag.upload(diag, c.stream);
   S.val.alloc_padded(S.nnz, 16, c.stream);
-  c.Dvec.alloc(c.n_u);
-  c.Dinv.alloc(c.n_u);
+  c.Dvec.alloc(c.nvec);   // full vector layout: the ghost entries of diag(F)^-1 arrive through the ghost import
+  c.Dinv.alloc(c.nvec);
+  c.Dvec.zero(c.stream); c.Dinv.zero(c.stream);
   NSX_CUDA(cudaStreamSynchronize(c.stream));
   tri_erase(c, NSX_BLOCK_S);
   c.S_symbolic = true;
@@ -99,11 +106,12 @@ void schur_symbolic(Ctx &c) {
 void schur_complement(Ctx &c) {
   schur_symbolic(c);
   extract_diag(c, c.F, c.Dvec.p, c.Dinv.p);
+  halo_exchange(c, 0, c.Dinv.p);
   const int wpb = 8;
   const size_t smem = (size_t)wpb * c.S.max_row * sizeof(double);
   if (smem > 48 * 1024) throw std::runtime_error("Schur complement row too long for the shared-memory accumulator");
   k_schur<<<(int)((c.n_p + wpb - 1) / wpb), wpb * 32, smem, c.stream>>>(c.n_p, c.B.rowptr.p, c.B.col.p, c.B.val.p, c.Dinv.p, c.Bt.rowptr.p,
-                                                                       c.Bt.col.p, c.Bt.val.p, c.S.rowptr.p, c.S.col.p, c.S.val.p, c.S.max_row);
+                                                                       c.Bt.col.p, c.Bt.val.p, c.S.rowptr.p, c.S.col.p, c.S.val.p, c.S.max_row, c.n_u, c.n_p);
   c.stat_launches++;
   NSX_CUDA(cudaGetLastError());
 }

@@ -51,9 +51,9 @@ struct PassHdr { int val_off, idx_off, ring16, wait; int tq, rrf, val_cnt, idx_c
 // NODE: a row is a velocity node and stands for the vector entries (2 row, 2 row + 1); one matrix value serves both components
 template <bool SGS, bool NODE>
 __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_sweep_block(const BlkDesc *__restrict__ blks, const PassHdr *__restrict__ passes, const double *__restrict__ bl_val,
-                                                        const uint16_t *__restrict__ bl_idx, const int32_t *__restrict__ perm, const double *__restrict__ x,
-                                                        double *__restrict__ y, const double *__restrict__ scale, double *__restrict__ v_out,
-                                                        const int *__restrict__ gate, int max_rows, int max_pass, int ring_bytes) {
+                                                        const uint16_t *__restrict__ bl_idx, const int32_t *__restrict__ perm, const int32_t *__restrict__ perm_y,
+                                                        const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ scale,
+                                                        double *__restrict__ v_out, const int *__restrict__ gate, int max_rows, int max_pass, int ring_bytes) {
   if (gate && *gate != 0) return;
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: ring, work vector (+ 8 zero slots for padding rows / entries), pass headers, barriers
@@ -74,9 +74,10 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_sweep_block(const BlkDesc
     if (scale) { const double a = *scale; inv = isfinite(a) ? 1.0 / a : 0.0; }
     for (int i = tid; i < B.nrows; i += NT) {
       const int32_t g = perm[B.row0 + i];
-      if (NODE) {
-        double2 v = reinterpret_cast<const double2 *>(x)[g];
-        if (scale) { v.x = inv * v.x; v.y = inv * v.y; reinterpret_cast<double2 *>(v_out)[g] = v; }
+      if (NODE) {   // perm / perm_y: the vector entries of the node's two components
+        const int32_t gy = perm_y[B.row0 + i];
+        double2 v = make_double2(x[g], x[gy]);
+        if (scale) { v.x = inv * v.x; v.y = inv * v.y; v_out[g] = v.x; v_out[gy] = v.y; }
         reinterpret_cast<double2 *>(xs)[i] = v;
       } else {
         double v = x[g];
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_sweep_block(const BlkDesc
     if (flags & 2) asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");   // the level's results are visible to the next level
   }
   for (int i = tid; i < B.nrows; i += NC) {
-    if (NODE) reinterpret_cast<double2 *>(y)[perm[B.row0 + i]] = reinterpret_cast<const double2 *>(xs)[i];
+    if (NODE) { const double2 v = reinterpret_cast<const double2 *>(xs)[i]; y[perm[B.row0 + i]] = v.x; y[perm_y[B.row0 + i]] = v.y; }
     else y[perm[B.row0 + i]] = xs[i];
   }
 }
@@ -226,8 +227,14 @@ void rcb(std::vector<Pt> &pts, int64_t lo, int64_t hi, int parts, int first, std
 
 }  // namespace
 
-int geometric_blocks(Ctx &c, int block, const std::vector<int64_t> &rowptr, int64_t lo, int64_t hi, int first_group, std::vector<int32_t> &grp, int stride) {
+int geometric_blocks(Ctx &c, int block, const std::vector<int64_t> &rowptr, int64_t lo, int64_t hi, int first_group, std::vector<int32_t> &grp,
+                     const std::vector<int32_t> *row_dof) {
   const int64_t n = hi - lo;
+  std::vector<int32_t> dof_row;   // node rows: dof -> row (the x dof of a node names it)
+  if (row_dof) {
+    dof_row.assign(c.n_u + c.n_ug, -1);
+    for (size_t r = 0; r < row_dof->size(); ++r) dof_row[(*row_dof)[r]] = (int32_t)r;
+  }
   const bool pressure = block != NSX_BLOCK_F;
   const int64_t off = pressure ? c.n_u + c.n_ug : 0;           // position of the block's dofs in the cell table's numbering
   const int64_t nloc = pressure ? c.n_p + c.n_pg : c.n_u + c.n_ug;
@@ -241,8 +248,8 @@ int geometric_blocks(Ctx &c, int block, const std::vector<int64_t> &rowptr, int6
     cx /= nv; cy /= nv;
     for (int k = 0; k < nd; ++k) {
       int64_t d = (int64_t)c.h_cell_dofs[(size_t)cell * nd + k] - off;
-      if (d < 0 || d >= nloc || (stride == 2 && (d & 1))) continue;   // node rows take the position of their x component
-      d /= stride;
+      if (d < 0 || d >= nloc) continue;
+      if (row_dof) { d = dof_row[d]; if (d < 0) continue; }   // node rows take the position of their x dof
       if (d < lo || d >= hi) continue;
       sx[d - lo] += cx; sy[d - lo] += cy; cnt[d - lo]++;
     }
@@ -455,12 +462,14 @@ void bl_refresh(Ctx &c, TriPlan &P, bool sgs) {
   P.bl_sgs = sgs ? 1 : 0;
 }
 
-void bl_sweep(Ctx &c, TriPlan &P, bool sgs, double *y, const double *x, const double *scale, double *v_out, const int *gate) {
+void bl_sweep(Ctx &c, TriPlan &P, bool sgs, double *y, const double *x, const double *scale, double *v_out, const int *gate, bool node_layout) {
   if (P.bl_sgs != (sgs ? 1 : 0)) throw std::logic_error("block-local sweep: the stream does not hold the values of this preconditioner");
   if (!P.nblk || !P.n) return;
   const size_t smem = (size_t)P.bl_ring + bl_fixed_smem(P.bl_max_rows, P.bl_max_pass, P.node);
-  if (P.node && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)v_out) & 15)) throw std::logic_error("block-local sweep on velocity nodes needs 16-byte aligned vectors");
-  typedef void (*Kernel)(const BlkDesc *, const PassHdr *, const double *, const uint16_t *, const int32_t *, const double *, double *, const double *, double *, const int *, int, int, int);
+  if (node_layout && !P.node) throw std::logic_error("only a node plan works on vectors in the node layout");
+  const int32_t *px = P.node ? (node_layout ? P.px_node.p : P.px_ref.p) : P.perm.p, *py = P.node ? (node_layout ? P.py_node.p : P.py_ref.p) : nullptr;
+  typedef void (*Kernel)(const BlkDesc *, const PassHdr *, const double *, const uint16_t *, const int32_t *, const int32_t *, const double *, double *, const double *, double *,
+                         const int *, int, int, int);
   const int which = (sgs ? 1 : 0) + (P.node ? 2 : 0);
   const Kernel kernels[4] = {k_sweep_block<false, false>, k_sweep_block<true, false>, k_sweep_block<false, true>, k_sweep_block<true, true>};
   static std::map<std::pair<int, int>, size_t> attr;   // (device, kernel) -> limit already granted
@@ -470,7 +479,7 @@ void bl_sweep(Ctx &c, TriPlan &P, bool sgs, double *y, const double *x, const do
     lim = smem;
   }
   const PassHdr *ph = reinterpret_cast<const PassHdr *>(P.bl_pass.p);
-  kernels[which]<<<P.nblk, NT, smem, c.stream>>>(P.bl_blk.p, ph, P.bl_val.p, P.bl_idx.p, P.perm.p, x, y, scale, v_out, gate, P.bl_max_rows, P.bl_max_pass, P.bl_ring);
+  kernels[which]<<<P.nblk, NT, smem, c.stream>>>(P.bl_blk.p, ph, P.bl_val.p, P.bl_idx.p, px, py, x, y, scale, v_out, gate, P.bl_max_rows, P.bl_max_pass, P.bl_ring);
   c.stat_launches++;
 }
 

@@ -489,8 +489,7 @@ TriPlan &tri_plan(Ctx &c, int block, int variant, int ordering) {
     V.rp = &V.own_rp; V.col = &V.own_col;
   }
   struct { int64_t nrows, ncols; const std::vector<int64_t> &h_rowptr; const std::vector<int32_t> &h_col; } A{V.nrows, V.ncols, *V.rp, *V.col};
-  std::vector<int64_t> owned = (block == NSX_BLOCK_F) ? c.owned_u : c.owned_p;
-  if (variant == 2) for (int64_t &o : owned) o /= 2;
+  const std::vector<int64_t> &owned = variant == 2 ? c.owned_nodes : (block == NSX_BLOCK_F) ? c.owned_u : c.owned_p;
   std::unique_ptr<TriPlan> up(new TriPlan);
   TriPlan &P = *up;
   P.ordering = ord;
@@ -505,7 +504,7 @@ TriPlan &tri_plan(Ctx &c, int block, int variant, int ordering) {
   if (ord >= 2) {
     int ng = 0;
     for (size_t r = 0; r + 1 < owned.size(); ++r)
-      if (owned[r + 1] > owned[r]) ng += geometric_blocks(c, block, A.h_rowptr, owned[r], owned[r + 1], ng, range, variant == 2 ? 2 : 1);
+      if (owned[r + 1] > owned[r]) ng += geometric_blocks(c, block, A.h_rowptr, owned[r], owned[r + 1], ng, range, variant == 2 ? &c.h_node_dx : nullptr);
     P.nblk = ng;
   } else {
     for (size_t r = 0; r + 1 < owned.size(); ++r)
@@ -638,6 +637,11 @@ TriPlan &tri_plan(Ctx &c, int block, int variant, int ordering) {
   P.work.alloc(n);
   P.yp.alloc(n);
   if (P.nblk) bl_build(c, P);
+  if (P.node) {   // the two vector entries of every (permuted) node row, in both layouts
+    std::vector<int32_t> a(n), b(n), cc(n), dd(n);
+    for (int64_t r = 0; r < n; ++r) { a[r] = c.h_node_dx[perm[r]]; b[r] = c.h_node_dy[perm[r]]; cc[r] = 2 * perm[r]; dd[r] = 2 * perm[r] + 1; }
+    P.px_ref.upload(a, c.stream); P.py_ref.upload(b, c.stream); P.px_node.upload(cc, c.stream); P.py_node.upload(dd, c.stream);
+  }
   NSX_CUDA(cudaStreamSynchronize(c.stream));
   c.tri[key] = std::move(up);
   return *c.tri[key];

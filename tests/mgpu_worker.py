@@ -52,7 +52,7 @@ def main():
     dev._ck(N.nsx().nsx_spmv(dev.h, N.BLOCK_J, N.VEC_TMP0, N.VEC_TMP1))
     y_d = gather_global(l, g, dev.download(N.VEC_TMP1))
     res_d = gather_global(l, g, dev.download(N.VEC_RESIDUAL))
-    rc_d, it_d, fr_d = dev.solve(N.STATIONARY, 1, prec, 1e-10, 3000)
+    rc_d, it_d, fr_d = dev.solve(N.STATIONARY, 1, prec, 1e-12, 3000)
     x_d = gather_global(l, g, dev.download(N.VEC_DELTA))
     dev.save_eval_point()
     dev.update(1.0)
@@ -68,10 +68,10 @@ def main():
         assert np.abs(res_d - o.vec(3)).max() <= 1e-11 * np.abs(o.vec(3)).max()
         y_o = o.spmv(N.BLOCK_J, x)
         assert np.abs(y_d - y_o).max() <= 1e-12 * np.abs(y_o).max()
-        rc_o, it_o, fr_o, _ = o.solve(N.STATIONARY, 1, prec, 1e-10, 3000)
+        rc_o, it_o, fr_o, _ = o.solve(N.STATIONARY, 1, prec, 1e-12, 3000)
         assert rc_o == 0 and rc_d == 0, (rc_o, rc_d)
         x_o = o.vec(2).copy()
-        assert np.linalg.norm(x_d - x_o) <= 1e-7 * np.linalg.norm(x_o), np.linalg.norm(x_d - x_o) / np.linalg.norm(x_o)
+        assert np.linalg.norm(x_d - x_o) <= 1e-8 * np.linalg.norm(x_o), np.linalg.norm(x_d - x_o) / np.linalg.norm(x_o)
         o.vec(0)[:] = sol + x_o
         r2_o = o.assemble(N.MODE_NEWTON, False, nu)
         assert abs(r2_d - r2_o) <= 1e-6 * max(r2_o, 1e-6), (r2_d, r2_o)

@@ -47,6 +47,7 @@ int nsx_create(int, int nranks, int, void *, nsx_ctx **out) {
 }
 int nsx_destroy(nsx_ctx *c) { if (c) { if (c->P) orc_destroy(c->P); delete c; } return NSX_OK; }
 const char *nsx_last_error(const nsx_ctx *c) { return c ? c->err.c_str() : "null context"; }
+int nsx_set_option(nsx_ctx *, int, int64_t) { return NSX_OK; }   // kernel / ordering choices have no meaning for the oracle
 int nsx_set_discretisation(nsx_ctx *c, int elem, int64_t n_cells, const double *cell_vertices, const uint32_t *cell_dofs, int64_t n_u, int64_t n_p) {
   c->P = orc_create(elem, (int)n_cells, cell_vertices, cell_dofs, n_u, n_p);
   c->n = n_u + n_p;

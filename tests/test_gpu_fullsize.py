@@ -64,12 +64,20 @@ def test_block_spmv_and_sgs_at_full_size(big):
     # linearity: J (a x + z) = a J x + J z
     lin = dev.spmv(N.BLOCK_J, 0.37 * x + z)
     assert np.abs(lin - (0.37 * ref + J @ z)).max() <= 1e-12 * np.abs(ref).max()
-    # multicolour SGS by definition: y = (D + U)^-1 D (D + L)^-1 x in the elimination order  <=>
-    # (D + L) D^-1 (D + U) y = x on the permuted matrix
+    # SGS by definition, default elimination order (CTA-local blocks, multicolour inside): y = (D + U)^-1 D (D + L)^-1 x on the
+    # block-diagonal part of F in the elimination order  <=>  (D + L) D^-1 (D + U) y = x on the permuted, block-filtered matrix
     xu = x[: d.n_u]
     y = dev.inner_apply(N.BLOCK_F, 0, xu)
-    perm = dev.ordering(N.BLOCK_F)
-    Fp = F[perm][:, perm].tocsr()
+    off, perm = dev.sweep_blocks(N.BLOCK_F)
+    assert len(off) - 1 == 2 * 148 or len(off) - 1 >= 64      # two CTA-local blocks per SM on a B200
+    blk = np.empty(d.n_u, dtype=np.int64)
+    for b in range(len(off) - 1):
+        blk[perm[off[b]:off[b + 1]]] = b
+    Fc = F.tocoo()
+    keep = blk[Fc.row] == blk[Fc.col]
+    print("couplings kept by the block-local sweeps:", keep.mean())
+    Fb = sp.csr_matrix((Fc.data[keep], (Fc.row[keep], Fc.col[keep])), shape=F.shape)
+    Fp = Fb[perm][:, perm].tocsr()
     Dg = Fp.diagonal()
     Lo, Up = sp.tril(Fp, -1, format="csr"), sp.triu(Fp, 1, format="csr")
     yp = y[perm]
@@ -85,7 +93,7 @@ import numpy as np, scipy.sparse as sp
 sys.path.insert(0, os.path.join(os.environ["NSX_ROOT"], "tests")); sys.path.insert(0, os.environ["NSX_ROOT"])
 import nsxlib as N
 d = N.Disc.generate(300, 100)
-dev = N.Device(d)
+dev = N.Device(d, ordering=1)   # the colour-phased persistent kernel of elimination order 1
 dev.upload(N.VEC_SOLUTION, N.synthetic_state(d, 1234))
 dev.assemble(N.MODE_NEWTON, False, 1 / 90.0)
 F = dev.csr(N.BLOCK_F)

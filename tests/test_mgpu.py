@@ -15,10 +15,11 @@ def _ngpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("elem,prec", [("tri", 0), ("quad", 1), ("quad", 0)])
+@pytest.mark.parametrize("elem,prec", [("tri", 0), ("quad", 1), ("quad", 0), ("quad", 2), ("tri", 2)])
 def test_two_gpu_run_matches_global_oracle(elem, prec):
-    """blockDiagonal (SGS) and blockTriangular (AMG + ILU) on two ranks; aSIMPLE on a partitioned system needs the ghost rows of
-    Bt for the Schur product and answers NSX_E_STATE in this round."""
+    """blockDiagonal (SGS), blockTriangular (AMG + ILU) and aSIMPLE on two ranks.  aSIMPLE: the ghost rows of Bt are assembled
+    redundantly from the ghost-layer cells, S = B diag(F)^-1 Bt is formed for the rank-local block (ILU) and applied as
+    B (diag(F)^-1 (Bt x)) with two ghost imports in the CG solve."""
     if _ngpus() < 2:
         pytest.skip("needs two GPUs")
     worker = os.path.join(N.ROOT, "tests", "mgpu_worker.py")
