@@ -54,6 +54,8 @@ enum nsx_option {
                              2 (default): when moreover F(u_x a, u_x b) == F(u_y a, u_y b) bit for bit, i.e. F = K (x) I_2, one scalar
                              matrix over the velocity nodes serves both components in the SpMV and in the SGS / ILU(0) sweeps
                              (orderings 2 and 3); 0: always the full pattern */
+  NSX_OPT_L2_HINTS = 8,   /* 1 (default): the TMA copies of matrix values / columns carry an evict-first L2 policy, so that the streams
+                             (read once per launch) do not push the Krylov basis out of the 126 MB L2; 0: no hint */
   NSX_OPT_HOST_INNER = 6  /* 1: the inner FGMRES solves run their recurrences on the host (one stream synchronisation per
                              iteration, round-1 behaviour); 0 (default): device-side Givens / convergence decision, the host
                              polls a mapped record and launches the next sweep speculatively */

@@ -144,6 +144,7 @@ int nsx_set_option(nsx_ctx *ctx, int option, int64_t value) {
         if (value < 0 || value > 3) throw std::invalid_argument("SpMV kernel must be 0, 1, 2 or 3");
         ctx->stream_spmv = (int)value; break;
       case NSX_OPT_HOST_INNER: ctx->host_inner = value != 0; break;
+      case NSX_OPT_L2_HINTS: ctx->l2_hints = value != 0; break;
       case NSX_OPT_DECOUPLE:
         if (value < 0 || value > 2) throw std::invalid_argument("decouple must be 0 (off), 1 (same-component view) or 2 (node view where it holds)");
         ctx->decouple = value != 0; ctx->decouple_nodes = value == 2; ctx->dec_epoch = 0; break;

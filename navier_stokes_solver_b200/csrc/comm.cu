@@ -88,14 +88,15 @@ __global__ void k_pack(int64_t n, const int32_t *__restrict__ idx, const double 
 
 }  // namespace
 
-void halo_exchange(Ctx &c, int blk, const double *base_) {
+void halo_exchange(Ctx &c, int blk, const double *base_, bool node_layout) {
   HaloPlan &H = blk ? c.halo_p : c.halo_u;
   if (!c.comm || H.nbr.empty()) return;
   Nccl &N = nccl();
   double *base = const_cast<double *>(base_);  // the ghost tail of an input vector is scratch by construction
   double *ghost = blk ? base + c.n_p + c.n_ug : base + c.n;
   if (H.nsend) {
-    k_pack<<<(int)((H.nsend + 255) / 256), 256, 0, c.stream>>>(H.nsend, H.send_idx.p, base, H.send_buf.p);
+    if (node_layout && (blk != 0 || !H.send_idx_node.p)) throw std::logic_error("no ghost import plan for the node layout");
+    k_pack<<<(int)((H.nsend + 255) / 256), 256, 0, c.stream>>>(H.nsend, node_layout ? H.send_idx_node.p : H.send_idx.p, base, H.send_buf.p);
     c.stat_launches++;
   }
   ncclComm_t comm = (ncclComm_t)c.comm;

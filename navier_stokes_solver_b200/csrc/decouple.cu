@@ -93,35 +93,44 @@ static void build_decoupled(Ctx &c) {
 // pairs are not adjacent in general.  Nodes are numbered by ascending dx.  Row dx(a) of F restricted to x columns and row dy(a)
 // restricted to y columns must hit the same nodes: then K(a, b) = F(dx a, dx b) = F(dy a, dy b) is one scalar matrix (if the values
 // agree, checked per assembly), kept as Kn with columns in the NODE LAYOUT of a vector: entry 2b = x component of node b, 2b + 1 = y.
-// One rank only for now: the node layout has no ghost import.
+// On a partitioned system only the owned entries of a vector are permuted; its ghost tail keeps the reference order, a ghost node's
+// pair is addressed through a small table (negative column ids), and the ghost import packs from node-layout positions.
 static void build_node_view(Ctx &c) {
   c.node_struct = -1;
-  if (c.n_ug || c.n_pg || (c.n_u & 1)) return;
+  if (c.n_u & 1) return;
   const std::vector<uint8_t> &comp = velocity_components(c);
   const DevCSR &F = c.F;
-  const int64_t n = F.nrows;
+  const int64_t n = F.nrows, nloc = c.n_u + c.n_ug;
   const FETables &T = c.fe;
   const int nd = T.ndofs;
-  std::vector<int32_t> partner(n, -1);
+  std::vector<int32_t> partner(nloc, -1);
   {
     int ldv[MAX_VN][2];
     for (int i = 0; i < nd; ++i) if (T.dof_comp[i] < 2) ldv[T.dof_node[i]][T.dof_comp[i]] = i;
     for (int64_t cell = 0; cell < c.ncells; ++cell)
       for (int a = 0; a < T.nvn; ++a) {
         const int64_t dx = c.h_cell_dofs[(size_t)cell * nd + ldv[a][0]], dy = c.h_cell_dofs[(size_t)cell * nd + ldv[a][1]];
-        if (dx >= n || dy >= n) return;
+        if (dx >= nloc || dy >= nloc || (dx < n) != (dy < n)) return;   // both components of a node have the same owner
         if ((partner[dx] >= 0 && partner[dx] != dy) || (partner[dy] >= 0 && partner[dy] != dx)) return;
         partner[dx] = (int32_t)dy; partner[dy] = (int32_t)dx;
       }
   }
-  std::vector<int32_t> node_of(n, -1);
+  // owned nodes first (ascending x dof), then the ghost nodes (ascending x dof): ghost node g has column id nn + g on the host
+  std::vector<int32_t> node_of(nloc, -1);
   c.h_node_dx.clear(); c.h_node_dy.clear();
-  for (int64_t d = 0; d < n; ++d) {
+  std::vector<int2> gpair;
+  for (int64_t d = 0; d < nloc; ++d) {
     if (partner[d] < 0) return;
-    if (comp[d] == 0) { node_of[d] = (int32_t)c.h_node_dx.size(); c.h_node_dx.push_back((int32_t)d); c.h_node_dy.push_back(partner[d]); }
+    if (comp[d] != 0) continue;
+    if (d < n) { node_of[d] = (int32_t)c.h_node_dx.size(); c.h_node_dx.push_back((int32_t)d); c.h_node_dy.push_back(partner[d]); }
   }
   const int64_t nn = (int64_t)c.h_node_dx.size();
   if (2 * nn != n) return;
+  for (int64_t d = n; d < nloc; ++d)
+    if (comp[d] == 0) {   // a ghost pair sits in the ghost tail of a vector, behind the owned pressure entries
+      node_of[d] = (int32_t)(nn + (int64_t)gpair.size());
+      gpair.push_back(make_int2((int)(d + c.n_p), (int)(partner[d] + c.n_p)));
+    }
   // preconditioner ranges (nsx_set_ranks) must hold whole nodes
   c.owned_nodes.assign(c.owned_u.size(), 0);
   for (size_t r = 0; r + 1 < c.owned_u.size(); ++r) {
@@ -133,7 +142,7 @@ static void build_node_view(Ctx &c) {
     c.owned_nodes[r + 1] = c.owned_nodes[r] + cnt;
   }
   DevCSR &K = c.Kn;
-  K.nrows = nn; K.ncols = nn; K.row0 = 0;
+  K.nrows = nn; K.ncols = nn + (int64_t)gpair.size(); K.row0 = 0;
   K.h_rowptr.assign(nn + 1, 0);
   K.h_col.clear();
   std::vector<int64_t> sx, sy;
@@ -150,8 +159,9 @@ static void build_node_view(Ctx &c) {
       const int32_t cy = partner[cx];
       const int32_t *it = std::lower_bound(yb, ye, cy);
       if (it == ye || *it != cy) return;
-      K.h_col.push_back(node_of[cx]);
-      dev_col.push_back(2 * node_of[cx]);
+      const int32_t b = node_of[cx];
+      K.h_col.push_back(b);
+      dev_col.push_back(b < nn ? 2 * b : -(int32_t)(b - nn) - 1);   // owned: position of the pair in the node layout; ghost: -(pair id) - 1
       sx.push_back(kx); sy.push_back(F.h_rowptr[ry] + (it - yb));
       --ny;
     }
@@ -171,6 +181,18 @@ static void build_node_view(Ctx &c) {
   c.h_Kn_src = sx;
   c.node_dx.upload(c.h_node_dx, c.stream);
   c.node_dy.upload(c.h_node_dy, c.stream);
+  c.node_gpair.upload(gpair, c.stream);
+  // ghost import of a vector in the node layout: the owned entries a neighbour needs, at their node-layout positions
+  if (c.halo_u.nsend) {
+    std::vector<int32_t> ref(c.halo_u.nsend), pos(c.halo_u.nsend);
+    NSX_CUDA(cudaMemcpyAsync(ref.data(), c.halo_u.send_idx.p, ref.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    NSX_CUDA(cudaStreamSynchronize(c.stream));
+    for (size_t k = 0; k < ref.size(); ++k) {
+      const int32_t d = ref[k];
+      pos[k] = comp[d] == 0 ? 2 * node_of[d] : 2 * node_of[partner[d]] + 1;
+    }
+    c.halo_u.send_idx_node.upload(pos, c.stream);
+  }
   NSX_CUDA(cudaStreamSynchronize(c.stream));
   c.node_struct = 1;
 }

@@ -146,6 +146,7 @@ struct HaloPlan {
   std::vector<int> nbr;                 // neighbour ranks
   std::vector<int64_t> send_ptr, recv_ptr;
   DevBuf<int32_t> send_idx;             // owned local ids to pack, grouped by neighbour
+  DevBuf<int32_t> send_idx_node;        // the same entries at their positions in the node layout of a vector (decouple.cu)
   DevBuf<double> send_buf;
   int64_t nsend = 0;
 };
@@ -157,6 +158,7 @@ struct Ctx {
   std::string err;
   int verbose = 0;
   int ordering = 2;      // ILU / SGS elimination order: 0 natural (Ifpack), 1 multicolour over the owned range, 2 (default) multicolour inside CTA-local blocks
+  bool l2_hints = true;   // NSX_OPT_L2_HINTS: TMA matrix streams carry an evict-first L2 policy
   bool ordering_auto = true;   // NSX_OPT_ORDERING never set: preconditioners that are a single ILU(0) application per iteration use ordering 3
   int block_rows = 0;    // ordering 2: target rows per block (0: n / #SMs clamped to [512, 4096])
   bool host_inner = false;  // inner FGMRES recurrences on the host (round-1 behaviour) instead of the device
@@ -212,6 +214,7 @@ struct Ctx {
   std::vector<int64_t> h_Kn_src;
   std::vector<int32_t> h_node_dx, h_node_dy;   // the two dofs of every velocity node (nodes numbered by ascending x dof)
   DevBuf<int32_t> node_dx, node_dy;
+  DevBuf<int2> node_gpair;                     // ghost nodes: positions of their (x, y) entries in a vector's ghost tail
   std::vector<int64_t> owned_nodes;            // owned_u in nodes
   DevBuf<double> node_b, node_x;               // right-hand side / iterate of an inner solve in the node layout
   int node_struct = 0;             // 0 not examined, 1 the numbering pairs up, -1 it does not
@@ -381,7 +384,7 @@ void amg_apply(Ctx &c, double *y, const double *x);
 // ---- comm.cu --------------------------------------------------------------------------------
 // blk 0: velocity ghosts of the vector starting at `base` (block or velocity-only vector);
 // blk 1: pressure ghosts of the pressure part starting at `base`.  No-ops on one GPU.
-void halo_exchange(Ctx &c, int blk, const double *base);
+void halo_exchange(Ctx &c, int blk, const double *base, bool node_layout = false);   // node_layout: the owned velocity entries sit in the node layout
 void allreduce_slots(Ctx &c, int slot, int count);   // in-place sum over ranks of device scalar slots
 void comm_destroy(Ctx &c);
 

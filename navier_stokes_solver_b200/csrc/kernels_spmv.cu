@@ -109,6 +109,7 @@ struct StreamMat {
   const double *x;
   const int32_t *pcol = nullptr;  // paired columns (one even column id per two adjacent non-zeros), or null
   int node = 0;                   // rows are velocity nodes: y(2r, 2r+1) = sum_k val_k * x(col_k, col_k + 1)
+  const int2 *gpair = nullptr;    // node rows: a column id c < 0 is the ghost node -c - 1, whose pair sits at x[gpair.x], x[gpair.y]
 };
 
 __device__ __forceinline__ void stream_rows(const int32_t *__restrict__ rb, int b, const StreamMat &A1, const StreamMat &A2, bool two,
@@ -282,8 +283,15 @@ __device__ __forceinline__ void direct_rows(const TmaStage &S, const RowBlockDes
 
 // NODE consumer: the matrix is the scalar K of F = K (x) I_2 over the velocity nodes, vectors are in the node layout (entry 2b / 2b + 1
 // = x / y component of node b): a column id is 2b (16-byte aligned), one value multiplies the (x, y) pair, a row writes a pair.
+__device__ __forceinline__ double2 node_pair(const double *__restrict__ x, const int2 *__restrict__ gp, int c) {
+  if (c >= 0) return __ldg(reinterpret_cast<const double2 *>(x + c));
+  const int2 g = __ldg(gp + (-c - 1));
+  return make_double2(__ldg(x + g.x), __ldg(x + g.y));
+}
+
 template <int DLX>
-__device__ __forceinline__ void direct_rows_node(const TmaStage &S, const RowBlockDesc &d, const double *__restrict__ x1, double *__restrict__ yy, int add, int tid) {
+__device__ __forceinline__ void direct_rows_node(const TmaStage &S, const RowBlockDesc &d, const double *__restrict__ x1, const int2 *__restrict__ gp,
+                                                 double *__restrict__ yy, int add, int tid) {
   const double *v = S.val;
   const int32_t *cidx = S.col;
   const int64_t s1 = d.a1;
@@ -297,8 +305,8 @@ __device__ __forceinline__ void direct_rows_node(const TmaStage &S, const RowBlo
     for (int k = b1 + sl; k - sl < e1; k += 4 * DLX) {
       const bool p0 = k < e1, p1 = k + DLX < e1, p2 = k + 2 * DLX < e1, p3 = k + 3 * DLX < e1;
       const int c0 = p0 ? cidx[k] : 0, c1 = p1 ? cidx[k + DLX] : 0, c2 = p2 ? cidx[k + 2 * DLX] : 0, c3 = p3 ? cidx[k + 3 * DLX] : 0;
-      const double2 x0 = p0 ? __ldg(reinterpret_cast<const double2 *>(x1 + c0)) : z, xb = p1 ? __ldg(reinterpret_cast<const double2 *>(x1 + c1)) : z;
-      const double2 xc = p2 ? __ldg(reinterpret_cast<const double2 *>(x1 + c2)) : z, xd = p3 ? __ldg(reinterpret_cast<const double2 *>(x1 + c3)) : z;
+      const double2 x0 = p0 ? node_pair(x1, gp, c0) : z, xb = p1 ? node_pair(x1, gp, c1) : z;
+      const double2 xc = p2 ? node_pair(x1, gp, c2) : z, xd = p3 ? node_pair(x1, gp, c3) : z;
       const double v0 = p0 ? v[k] : 0.0, vb = p1 ? v[k + DLX] : 0.0, vc = p2 ? v[k + 2 * DLX] : 0.0, vd = p3 ? v[k + 3 * DLX] : 0.0;
       ax += v0 * x0.x; ay += v0 * x0.y; bx += vb * xb.x; by += vb * xb.y;
       ax += vc * xc.x; ay += vc * xc.y; bx += vd * xd.x; by += vd * xd.y;
@@ -319,10 +327,11 @@ __device__ __forceinline__ void direct_rows_node(const TmaStage &S, const RowBlo
 template <bool DIRECT>
 __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, int first, int stride, int nb, const StreamMat *M,
                                          double *__restrict__ y, int64_t yoff1, int add, unsigned char *ring, uint64_t *full, uint64_t *empty,
-                                         RowBlockDesc *pdesc) {
+                                         RowBlockDesc *pdesc, int l2_hints) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int nit = first < nb ? (nb - first + stride - 1) / stride : 0;
   if (tid >= TCONS) {
+    const uint64_t policy = l2_policy_evict_first();   // matrix streams are read once per product: leave the L2 to the vectors
     // producer warp: descriptors are fetched 32 at a time by the whole warp, lane 0 feeds the ring
     for (int it0 = 0; it0 < nit; it0 += 32) {
       __syncwarp();
@@ -353,7 +362,7 @@ __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, 
           mbar_expect_tx(&full[st], (uint32_t)d.c1 * (A1.pcol ? 10u : 12u) + (two ? (uint32_t)d.c2 * 12u : 0u) + (uint32_t)rc * 8u * (two ? 2u : 1u) +
                                         (uint32_t)sizeof(RowBlockDesc));
         __syncwarp();
-        if (bytes) bulk_g2s(dst, src, bytes, &full[st]);
+        if (bytes) { if (l2_hints) bulk_g2s_hint(dst, src, bytes, &full[st], policy); else bulk_g2s(dst, src, bytes, &full[st]); }
       }
     }
     return;
@@ -374,7 +383,7 @@ __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, 
     if (DIRECT) {
       // lanes per row follow the block's mean row length (host-side choice): four predicated entries per lane and trip
       if (M[0].node) {
-        if (d.lanes >= 8) direct_rows_node<8>(S, d, x1, yy, add, tid); else direct_rows_node<4>(S, d, x1, yy, add, tid);
+        if (d.lanes >= 8) direct_rows_node<8>(S, d, x1, M[0].gpair, yy, add, tid); else direct_rows_node<4>(S, d, x1, M[0].gpair, yy, add, tid);
       } else if (paired) direct_rows<NSX_DL / 2, true>(S, d, two, x1, x2, yy, add, tid);
       else if (d.lanes >= 16) direct_rows<16, false>(S, d, two, x1, x2, yy, add, tid);
       else if (d.lanes == 8) direct_rows<8, false>(S, d, two, x1, x2, yy, add, tid);
@@ -419,7 +428,7 @@ __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, 
 // velocity rows (F + Bt, kind 0) come first in the list, then those of the pressure rows (B, kind 1)
 template <bool DIRECT>
 __global__ void __launch_bounds__(TCONS + 32, NSX_TMINB) k_spmv_tma(const RowBlockDesc *__restrict__ desc, int nb, StreamMat M0, StreamMat M1, StreamMat M2,
-                                                            double *__restrict__ y, int64_t yoff1, int add) {
+                                                            double *__restrict__ y, int64_t yoff1, int add, int l2_hints) {
   extern __shared__ __align__(128) unsigned char tma_smem[];
   __shared__ RowBlockDesc pdesc[32];
   __shared__ StreamMat M[3];
@@ -430,7 +439,7 @@ __global__ void __launch_bounds__(TCONS + 32, NSX_TMINB) k_spmv_tma(const RowBlo
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  tma_rows<DIRECT>(desc, blockIdx.x, gridDim.x, nb, M, y, yoff1, add, tma_smem, full, empty, pdesc);
+  tma_rows<DIRECT>(desc, blockIdx.x, gridDim.x, nb, M, y, yoff1, add, tma_smem, full, empty, pdesc, l2_hints);
 }
 
 void append_row_descs(std::vector<RowBlockDesc> &h, const DevCSR &A1, const DevCSR *A2, int kind) {
@@ -516,7 +525,7 @@ inline int pick_group(const DevCSR &A) {
 
 void spmv(Ctx &c, const DevCSR &A_, const double *x, double *y, bool add) {
   // ghost import of the input first (no-op on one GPU): a rank that owns no row of this block still has to post its sends
-  halo_exchange(c, (&A_ == &c.F || &A_ == &c.B || &A_ == &c.Fd || &A_ == &c.Kn) ? 0 : 1, x);
+  halo_exchange(c, (&A_ == &c.F || &A_ == &c.B || &A_ == &c.Fd || &A_ == &c.Kn) ? 0 : 1, x, &A_ == &c.Kn);
   if (!A_.nrows) return;
   spmv_local(c, A_, x, y, add);
 }
@@ -536,10 +545,10 @@ void spmv_local(Ctx &c, const DevCSR &A_, const double *x, double *y, bool add) 
     StreamMat M{A.rowptr.p, A.col.p, A.val.p, x, (&A_ == &c.F || &A_ == &c.B) ? pairs_for(c, A_, x) : nullptr};
     if (&A_ == &c.Kn) {
       if (c.stream_spmv != 3 || (((uintptr_t)x | (uintptr_t)y) & 15)) throw std::logic_error("the node view of F needs the direct TMA SpMV and 16-byte aligned vectors");
-      M.node = 1;
+      M.node = 1; M.gpair = c.node_gpair.p;
     }
-    if (c.stream_spmv == 3) k_spmv_tma<true><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0);
-    else k_spmv_tma<false><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0);
+    if (c.stream_spmv == 3) k_spmv_tma<true><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0, c.l2_hints ? 1 : 0);
+    else k_spmv_tma<false><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0, c.l2_hints ? 1 : 0);
     c.stat_launches++; c.stat_spmv++;
     return;
   }
@@ -574,8 +583,8 @@ void block_spmv(Ctx &c, const double *x, double *y) {
     const int grid = std::min(c.ndesc_u, NSX_TMINB * c.num_sms);
     const StreamMat MF{c.F.rowptr.p, c.F.col.p, c.F.val.p, x, pairs_for(c, c.F, x)}, MBt{c.Bt.rowptr.p, c.Bt.col.p, c.Bt.val.p, x + c.n_u, nullptr},
         MB{c.B.rowptr.p, c.B.col.p, c.B.val.p, x, pairs_for(c, c.B, x)};
-    if (c.stream_spmv == 3) k_spmv_tma<true><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(c.desc_u.p, c.ndesc_u, MF, MBt, MB, y, c.n_u, 0);
-    else k_spmv_tma<false><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(c.desc_u.p, c.ndesc_u, MF, MBt, MB, y, c.n_u, 0);
+    if (c.stream_spmv == 3) k_spmv_tma<true><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(c.desc_u.p, c.ndesc_u, MF, MBt, MB, y, c.n_u, 0, c.l2_hints ? 1 : 0);
+    else k_spmv_tma<false><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(c.desc_u.p, c.ndesc_u, MF, MBt, MB, y, c.n_u, 0, c.l2_hints ? 1 : 0);
     c.stat_launches++; c.stat_spmv++;
     return;
   }

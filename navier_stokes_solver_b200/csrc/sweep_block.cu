@@ -53,7 +53,7 @@ template <bool SGS, bool NODE>
 __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_sweep_block(const BlkDesc *__restrict__ blks, const PassHdr *__restrict__ passes, const double *__restrict__ bl_val,
                                                         const uint16_t *__restrict__ bl_idx, const int32_t *__restrict__ perm, const int32_t *__restrict__ perm_y,
                                                         const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ scale,
-                                                        double *__restrict__ v_out, const int *__restrict__ gate, int max_rows, int max_pass, int ring_bytes) {
+                                                        double *__restrict__ v_out, const int *__restrict__ gate, int max_rows, int max_pass, int ring_bytes, int l2_hints) {
   if (gate && *gate != 0) return;
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: ring, work vector (+ 8 zero slots for padding rows / entries), pass headers, barriers
@@ -93,14 +93,20 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_sweep_block(const BlkDesc
     if (tid == NC) {
       const double *gval = bl_val + B.val_base;
       const uint16_t *gidx = bl_idx + B.idx_base;
+      const uint64_t policy = l2_policy_evict_first();   // the matrix stream is read once per application: keep the Krylov basis in L2
       for (int p = 0; p < B.npass; ++p) {
         const PassHdr h = hdr[p];
         if (h.wait >= 0) mbar_wait(&empty[h.wait % NSLOT], (h.wait / NSLOT) & 1);
         const int st = p % NSLOT;
         unsigned char *dst = smem + (size_t)h.ring16 * 16;
         mbar_expect_tx(&full[st], (uint32_t)h.val_cnt * 8u + (uint32_t)h.idx_cnt * 2u);
-        bulk_g2s(dst, gval + (uint32_t)h.val_off, (uint32_t)h.val_cnt * 8u, &full[st]);
-        bulk_g2s(dst + (size_t)h.val_cnt * 8, gidx + (uint32_t)h.idx_off, (uint32_t)h.idx_cnt * 2u, &full[st]);
+        if (l2_hints) {
+          bulk_g2s_hint(dst, gval + (uint32_t)h.val_off, (uint32_t)h.val_cnt * 8u, &full[st], policy);
+          bulk_g2s_hint(dst + (size_t)h.val_cnt * 8, gidx + (uint32_t)h.idx_off, (uint32_t)h.idx_cnt * 2u, &full[st], policy);
+        } else {
+          bulk_g2s(dst, gval + (uint32_t)h.val_off, (uint32_t)h.val_cnt * 8u, &full[st]);
+          bulk_g2s(dst + (size_t)h.val_cnt * 8, gidx + (uint32_t)h.idx_off, (uint32_t)h.idx_cnt * 2u, &full[st]);
+        }
       }
     }
     return;
@@ -469,7 +475,7 @@ void bl_sweep(Ctx &c, TriPlan &P, bool sgs, double *y, const double *x, const do
   if (node_layout && !P.node) throw std::logic_error("only a node plan works on vectors in the node layout");
   const int32_t *px = P.node ? (node_layout ? P.px_node.p : P.px_ref.p) : P.perm.p, *py = P.node ? (node_layout ? P.py_node.p : P.py_ref.p) : nullptr;
   typedef void (*Kernel)(const BlkDesc *, const PassHdr *, const double *, const uint16_t *, const int32_t *, const int32_t *, const double *, double *, const double *, double *,
-                         const int *, int, int, int);
+                         const int *, int, int, int, int);
   const int which = (sgs ? 1 : 0) + (P.node ? 2 : 0);
   const Kernel kernels[4] = {k_sweep_block<false, false>, k_sweep_block<true, false>, k_sweep_block<false, true>, k_sweep_block<true, true>};
   static std::map<std::pair<int, int>, size_t> attr;   // (device, kernel) -> limit already granted
@@ -479,7 +485,7 @@ void bl_sweep(Ctx &c, TriPlan &P, bool sgs, double *y, const double *x, const do
     lim = smem;
   }
   const PassHdr *ph = reinterpret_cast<const PassHdr *>(P.bl_pass.p);
-  kernels[which]<<<P.nblk, NT, smem, c.stream>>>(P.bl_blk.p, ph, P.bl_val.p, P.bl_idx.p, px, py, x, y, scale, v_out, gate, P.bl_max_rows, P.bl_max_pass, P.bl_ring);
+  kernels[which]<<<P.nblk, NT, smem, c.stream>>>(P.bl_blk.p, ph, P.bl_val.p, P.bl_idx.p, px, py, x, y, scale, v_out, gate, P.bl_max_rows, P.bl_max_pass, P.bl_ring, c.l2_hints ? 1 : 0);
   c.stat_launches++;
 }
 

@@ -48,8 +48,12 @@ CASES = [
     (N.UNSTEADY, 1, 1, N.MODE_UNSTEADY_NEWTON, "tri"),
     (N.UNSTEADY, 1, 2, N.MODE_UNSTEADY_NEWTON, "tri"),   # config 3: FGMRES + aSIMPLE, unsteady flavour
     (N.UNSTEADY, 0, 2, N.MODE_UNSTEADY_NEWTON, "quad"),
-    (N.UNSTEADY, 2, 2, N.MODE_UNSTEADY_FIRST, "quad"),
+    (N.UNSTEADY, 2, 2, N.MODE_UNSTEADY_FIRST, "quad"),   # BiCGStab with a FIXED preconditioner (single ILU applications): converges (369 its)
+    (N.UNSTEADY, 2, 2, N.MODE_UNSTEADY_NEWTON, "tri"),   # ... and here (63 its): the two cases that pin K3
 ]
+# BiCGStab around a preconditioner with inner Krylov solves (a different operator in every application) may stagnate, and the
+# reference would throw; these cases must NOT: their parity assertions are the ones that pin the BiCGStab restatement
+MUST_CONVERGE = {(N.UNSTEADY, 2, 2, N.MODE_UNSTEADY_FIRST, "quad"), (N.UNSTEADY, 2, 2, N.MODE_UNSTEADY_NEWTON, "tri")}
 
 
 @pytest.mark.parametrize("flavour,solver,prec,mode,elem", CASES)
@@ -60,11 +64,15 @@ def test_solve_matches_oracle(flavour, solver, prec, mode, elem):
     rc_d, it_d, fr_d = dev.solve(flavour, solver, prec, tol, 2000)
     print(f"oracle: rc {rc_o} it {it_o} res {fr_o:.3e} inner {inner.tolist()} | gpu: rc {rc_d} it {it_d} res {fr_d:.3e} "
           f"inner [{dev.stat('INNER_F')}, {dev.stat('INNER_S')}, {dev.stat('PRECOND_APPLIES')}]")
+    if (flavour, solver, prec, mode, elem) in MUST_CONVERGE or solver != 2:
+        assert rc_o == 0, "the oracle has to converge here: this case pins the solver's restatement"
     if rc_o == N.NSX_E_NOCONV:
         # BiCGStab with an inexact (inner-Krylov) preconditioner can stagnate: the reference would throw
         # SolverControl::NoConvergence here, and so must the device path
+        print("branch: both sides NoConvergence (stagnating BiCGStab around inner Krylov solves)")
         assert rc_d == N.NSX_E_NOCONV   # (the step at which NaN / the iteration cap is hit depends on rounding)
         return
+    print("branch: converged on both sides, parity assertions run")
     assert rc_o == 0 and rc_d == 0
     x_o, x_d = orc.vec(2), dev.download(N.VEC_DELTA)
     assert np.linalg.norm(x_d - x_o) <= 1e-8 * np.linalg.norm(x_o)
