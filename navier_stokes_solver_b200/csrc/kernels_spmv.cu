@@ -283,13 +283,14 @@ __device__ __forceinline__ void direct_rows(const TmaStage &S, const RowBlockDes
 
 // NODE consumer: the matrix is the scalar K of F = K (x) I_2 over the velocity nodes, vectors are in the node layout (entry 2b / 2b + 1
 // = x / y component of node b): a column id is 2b (16-byte aligned), one value multiplies the (x, y) pair, a row writes a pair.
+template <bool GHOSTS>
 __device__ __forceinline__ double2 node_pair(const double *__restrict__ x, const int2 *__restrict__ gp, int c) {
-  if (c >= 0) return __ldg(reinterpret_cast<const double2 *>(x + c));
+  if (!GHOSTS || c >= 0) return __ldg(reinterpret_cast<const double2 *>(x + c));
   const int2 g = __ldg(gp + (-c - 1));
   return make_double2(__ldg(x + g.x), __ldg(x + g.y));
 }
 
-template <int DLX>
+template <int DLX, bool GHOSTS>
 __device__ __forceinline__ void direct_rows_node(const TmaStage &S, const RowBlockDesc &d, const double *__restrict__ x1, const int2 *__restrict__ gp,
                                                  double *__restrict__ yy, int add, int tid) {
   const double *v = S.val;
@@ -305,8 +306,8 @@ __device__ __forceinline__ void direct_rows_node(const TmaStage &S, const RowBlo
     for (int k = b1 + sl; k - sl < e1; k += 4 * DLX) {
       const bool p0 = k < e1, p1 = k + DLX < e1, p2 = k + 2 * DLX < e1, p3 = k + 3 * DLX < e1;
       const int c0 = p0 ? cidx[k] : 0, c1 = p1 ? cidx[k + DLX] : 0, c2 = p2 ? cidx[k + 2 * DLX] : 0, c3 = p3 ? cidx[k + 3 * DLX] : 0;
-      const double2 x0 = p0 ? node_pair(x1, gp, c0) : z, xb = p1 ? node_pair(x1, gp, c1) : z;
-      const double2 xc = p2 ? node_pair(x1, gp, c2) : z, xd = p3 ? node_pair(x1, gp, c3) : z;
+      const double2 x0 = p0 ? node_pair<GHOSTS>(x1, gp, c0) : z, xb = p1 ? node_pair<GHOSTS>(x1, gp, c1) : z;
+      const double2 xc = p2 ? node_pair<GHOSTS>(x1, gp, c2) : z, xd = p3 ? node_pair<GHOSTS>(x1, gp, c3) : z;
       const double v0 = p0 ? v[k] : 0.0, vb = p1 ? v[k + DLX] : 0.0, vc = p2 ? v[k + 2 * DLX] : 0.0, vd = p3 ? v[k + 3 * DLX] : 0.0;
       ax += v0 * x0.x; ay += v0 * x0.y; bx += vb * xb.x; by += vb * xb.y;
       ax += vc * xc.x; ay += vc * xc.y; bx += vd * xd.x; by += vd * xd.y;
@@ -324,7 +325,9 @@ __device__ __forceinline__ void direct_rows_node(const TmaStage &S, const RowBlo
 
 // Row blocks `first, first + stride, ...` of a list whose entries are of kind 0 (matrices M[0] and, if it has
 // non-zeros there, M[1] share the rows; y offset 0) or kind 1 (matrix M[2] alone; y offset yoff1).
-template <bool DIRECT>
+// NODE: 0 general rows (paired / unpaired columns), 1 node rows on one rank, 2 node rows with ghost nodes -- separate instantiations
+// keep the register budget of 4 CTAs per SM for each
+template <bool DIRECT, int NODE>
 __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, int first, int stride, int nb, const StreamMat *M,
                                          double *__restrict__ y, int64_t yoff1, int add, unsigned char *ring, uint64_t *full, uint64_t *empty,
                                          RowBlockDesc *pdesc, int l2_hints) {
@@ -382,12 +385,12 @@ __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, 
     const int nr = d.r1 - d.r0, roff = d.r0 & 1;
     if (DIRECT) {
       // lanes per row follow the block's mean row length (host-side choice): four predicated entries per lane and trip
-      if (M[0].node) {
-        if (d.lanes >= 8) direct_rows_node<8>(S, d, x1, M[0].gpair, yy, add, tid); else direct_rows_node<4>(S, d, x1, M[0].gpair, yy, add, tid);
+      if (NODE) {
+        const int2 *gp = M[0].gpair;
+        if (d.lanes >= 8) direct_rows_node<8, NODE == 2>(S, d, x1, gp, yy, add, tid); else direct_rows_node<4, NODE == 2>(S, d, x1, gp, yy, add, tid);
       } else if (paired) direct_rows<NSX_DL / 2, true>(S, d, two, x1, x2, yy, add, tid);
       else if (d.lanes >= 16) direct_rows<16, false>(S, d, two, x1, x2, yy, add, tid);
-      else if (d.lanes == 8) direct_rows<8, false>(S, d, two, x1, x2, yy, add, tid);
-      else direct_rows<4, false>(S, d, two, x1, x2, yy, add, tid);
+      else direct_rows<8, false>(S, d, two, x1, x2, yy, add, tid);
     } else {
     // phase 1: products in place (every consumer thread busy, four independent gathers each)
 #pragma unroll 4
@@ -426,7 +429,7 @@ __device__ __forceinline__ void tma_rows(const RowBlockDesc *__restrict__ desc, 
 
 // y = A x (kind-0 blocks with one matrix), or jacobian_matrix.vmult with M = {F, Bt, B}: the row blocks of the
 // velocity rows (F + Bt, kind 0) come first in the list, then those of the pressure rows (B, kind 1)
-template <bool DIRECT>
+template <bool DIRECT, int NODE>
 __global__ void __launch_bounds__(TCONS + 32, NSX_TMINB) k_spmv_tma(const RowBlockDesc *__restrict__ desc, int nb, StreamMat M0, StreamMat M1, StreamMat M2,
                                                             double *__restrict__ y, int64_t yoff1, int add, int l2_hints) {
   extern __shared__ __align__(128) unsigned char tma_smem[];
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(TCONS + 32, NSX_TMINB) k_spmv_tma(const RowBlo
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  tma_rows<DIRECT>(desc, blockIdx.x, gridDim.x, nb, M, y, yoff1, add, tma_smem, full, empty, pdesc, l2_hints);
+  tma_rows<DIRECT, NODE>(desc, blockIdx.x, gridDim.x, nb, M, y, yoff1, add, tma_smem, full, empty, pdesc, l2_hints);
 }
 
 void append_row_descs(std::vector<RowBlockDesc> &h, const DevCSR &A1, const DevCSR *A2, int kind) {
@@ -509,8 +512,10 @@ inline const int32_t *pairs_for(Ctx &c, const DevCSR &A_, const double *x) {
 void tma_attr_once(const Ctx &c) {   // cudaFuncSetAttribute applies per device
   static std::vector<int> done;
   if (std::find(done.begin(), done.end(), c.device) != done.end()) return;
-  NSX_CUDA(cudaFuncSetAttribute(k_spmv_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
-  NSX_CUDA(cudaFuncSetAttribute(k_spmv_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+  NSX_CUDA(cudaFuncSetAttribute(k_spmv_tma<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+  NSX_CUDA(cudaFuncSetAttribute(k_spmv_tma<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+  NSX_CUDA(cudaFuncSetAttribute(k_spmv_tma<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+  NSX_CUDA(cudaFuncSetAttribute(k_spmv_tma<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
   done.push_back(c.device);
 }
 
@@ -545,10 +550,12 @@ void spmv_local(Ctx &c, const DevCSR &A_, const double *x, double *y, bool add) 
     StreamMat M{A.rowptr.p, A.col.p, A.val.p, x, (&A_ == &c.F || &A_ == &c.B) ? pairs_for(c, A_, x) : nullptr};
     if (&A_ == &c.Kn) {
       if (c.stream_spmv != 3 || (((uintptr_t)x | (uintptr_t)y) & 15)) throw std::logic_error("the node view of F needs the direct TMA SpMV and 16-byte aligned vectors");
-      M.node = 1; M.gpair = c.node_gpair.p;
+      M.node = 1; M.gpair = c.n_ug ? c.node_gpair.p : nullptr;
     }
-    if (c.stream_spmv == 3) k_spmv_tma<true><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0, c.l2_hints ? 1 : 0);
-    else k_spmv_tma<false><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0, c.l2_hints ? 1 : 0);
+    if (M.node && M.gpair) k_spmv_tma<true, 2><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0, c.l2_hints ? 1 : 0);
+    else if (M.node) k_spmv_tma<true, 1><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0, c.l2_hints ? 1 : 0);
+    else if (c.stream_spmv == 3) k_spmv_tma<true, 0><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0, c.l2_hints ? 1 : 0);
+    else k_spmv_tma<false, 0><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(A.desc.p, A.ndesc, M, M, M, y, 0, add ? 1 : 0, c.l2_hints ? 1 : 0);
     c.stat_launches++; c.stat_spmv++;
     return;
   }
@@ -583,8 +590,8 @@ void block_spmv(Ctx &c, const double *x, double *y) {
     const int grid = std::min(c.ndesc_u, NSX_TMINB * c.num_sms);
     const StreamMat MF{c.F.rowptr.p, c.F.col.p, c.F.val.p, x, pairs_for(c, c.F, x)}, MBt{c.Bt.rowptr.p, c.Bt.col.p, c.Bt.val.p, x + c.n_u, nullptr},
         MB{c.B.rowptr.p, c.B.col.p, c.B.val.p, x, pairs_for(c, c.B, x)};
-    if (c.stream_spmv == 3) k_spmv_tma<true><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(c.desc_u.p, c.ndesc_u, MF, MBt, MB, y, c.n_u, 0, c.l2_hints ? 1 : 0);
-    else k_spmv_tma<false><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(c.desc_u.p, c.ndesc_u, MF, MBt, MB, y, c.n_u, 0, c.l2_hints ? 1 : 0);
+    if (c.stream_spmv == 3) k_spmv_tma<true, 0><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(c.desc_u.p, c.ndesc_u, MF, MBt, MB, y, c.n_u, 0, c.l2_hints ? 1 : 0);
+    else k_spmv_tma<false, 0><<<grid, TCONS + 32, TMA_SMEM, c.stream>>>(c.desc_u.p, c.ndesc_u, MF, MBt, MB, y, c.n_u, 0, c.l2_hints ? 1 : 0);
     c.stat_launches++; c.stat_spmv++;
     return;
   }

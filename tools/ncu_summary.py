@@ -4,6 +4,8 @@
 
   python tools/ncu_summary.py report  gpurun_out/x.ncu-rep   > profiles/x.md
   python tools/ncu_summary.py launches gpurun_out/launches.csv > profiles/launches.md
+  python tools/ncu_summary.py traffic  gpurun_out/x.ncu-rep MESH ORDERING > profiles/ncu_traffic.json
+      (dram__bytes_read.sum + dram__bytes_write.sum per launch of the hot kernels: what bench.py reports as roofline.traffic)
 """
 import collections
 import csv
@@ -82,5 +84,32 @@ def launches(path):
         print(f"| {k} | {v[0]} | {v[1] / 1e6:.3f} | {100 * v[1] / tot:.2f} | {v[1] / v[0] / 1e3:.1f} |")
 
 
+def traffic(path, mesh, ordering):
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    head, units, body = rows[0], rows[1], rows[2:]
+    idx = {n: i for i, n in enumerate(head)}
+
+    def to_bytes(v, unit):
+        v = float(v.replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+    per = collections.defaultdict(list)
+    for r in body:
+        b = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+        per[short(r[idx["Kernel Name"]])].append(b)
+    names = {"sgs_F": "k_sweep_block", "spmv_F": "k_spmv_tma", "block_spmv": "k_spmv_tma"}
+    res = {}
+    for key, pat in names.items():
+        vals = [v for k, vs in per.items() if k.startswith(pat) for v in vs]
+        if not vals:
+            continue
+        # the Jacobian block product is the largest launch of the SpMV kernel, the F product of the inner solves the most frequent one
+        res[key] = max(vals) if key == "block_spmv" else sorted(vals)[len(vals) // 2]
+    print(json.dumps({"mesh": mesh, "ordering": int(ordering), "source": path.split("/")[-1], "how": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum per launch (median over the captured launches; block_spmv = the largest SpMV launch)",
+                      "bytes_per_launch": res, "all_kernels_median_bytes": {k: sorted(v)[len(v) // 2] for k, v in per.items()}}, indent=1))
+
+
 if __name__ == "__main__":
-    {"report": report, "launches": launches}[sys.argv[1]](sys.argv[2])
+    {"report": report, "launches": launches, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
