@@ -65,6 +65,7 @@ enum nsx_stat {
   NSX_STAT_LEVELS_F = 4, NSX_STAT_LEVELS_MP = 5, NSX_STAT_LEVELS_S = 6, NSX_STAT_SPMV_CALLS = 7,
   NSX_STAT_ASSEMBLY_COLOURS = 8, NSX_STAT_ASSEMBLY_TABLES = 9, NSX_STAT_LAST_STEP = 10,
   NSX_STAT_HALO_EXCHANGES = 11, NSX_STAT_ALLREDUCES = 12,
+  NSX_STAT_SWEEP_BYTES_F = 14, NSX_STAT_SPMV_BYTES_F = 15, /* stored bytes per launch of the F sweeps / the inner solves' F product */
   NSX_STAT_F_DECOUPLED = 13 /* view found by the last check of NSX_OPT_DECOUPLE: 0 full, 1 same-component, 2 nodes */
 };
 

@@ -174,6 +174,21 @@ int64_t nsx_get_stat(const nsx_ctx *ctx, int stat) {
     case NSX_STAT_LAST_STEP: return ctx->last_step;
     case NSX_STAT_HALO_EXCHANGES: return ctx->stat_halo;
     case NSX_STAT_ALLREDUCES: return ctx->stat_allreduce;
+    case NSX_STAT_SWEEP_BYTES_F: {   // stored bytes one application of the F sweeps streams: the plan of the view found by the last check
+      int view = (ctx->dec_epoch == ctx->matrix_epoch && ctx->dec_ok) ? (ctx->node_ok ? 2 : 1) : 0;
+      if (view == 2 && (ctx->ordering < 2 || ctx->stream_spmv != 3)) view = 1;
+      auto it = ctx->tri.find(NSX_BLOCK_F + 16 * view + 256 * ctx->ordering);
+      if (it == ctx->tri.end()) return 0;
+      const TriPlan &P = *it->second;
+      return P.nblk ? (int64_t)(P.bl_nval * 8 + (int64_t)P.bl_idx.n * 2) : (int64_t)P.nnz * 12;
+    }
+    case NSX_STAT_SPMV_BYTES_F: {    // stored matrix bytes one F product of the inner solves reads (values + columns)
+      int view = (ctx->dec_epoch == ctx->matrix_epoch && ctx->dec_ok) ? (ctx->node_ok ? 2 : 1) : 0;
+      if (view == 2 && (ctx->ordering < 2 || ctx->stream_spmv != 3)) view = 1;
+      if (view == 2) return ctx->Kn.nnz * 12;
+      if (view == 1) return ctx->Fd.nnz * 12;
+      return ctx->F.nnz * (ctx->F.pair_state == 1 ? 10 : 12);
+    }
     case NSX_STAT_F_DECOUPLED: return (ctx->dec_epoch == ctx->matrix_epoch && ctx->dec_ok) ? (ctx->node_ok ? 2 : 1) : 0;
   }
   return -1;

@@ -270,9 +270,12 @@ int geometric_blocks(Ctx &c, int block, const std::vector<int64_t> &rowptr, int6
   int64_t parts;
   if (c.block_rows > 0) parts = (n + c.block_rows - 1) / c.block_rows;
   else {
-    // BLOCKS_PER_SM co-resident CTAs per SM hide each other's level latency; blocks of 512 .. 2048 rows, whole waves above
-    const int64_t slots = (int64_t)std::max(1, c.num_sms) * BLOCKS_PER_SM, per = n / slots;
-    if (per <= 512) parts = std::min<int64_t>(slots, (n + 256) / 512);
+    // BLOCKS_PER_SM co-resident CTAs per SM hide each other's level latency; blocks of 512 .. 2048 rows, whole waves above.  On N
+    // ranks every rank cuts its own range: one block per SM there, so that the total number of blocks (and with it the strength of
+    // the block-Jacobi preconditioner) does not grow faster than the machine
+    const int per_sm = c.nranks > 1 ? 1 : BLOCKS_PER_SM;
+    const int64_t slots = (int64_t)std::max(1, c.num_sms) * per_sm, per = n / slots;
+    if (per <= 256) parts = std::min<int64_t>(slots, (n + 128) / 256);
     else parts = slots * ((per + 2047) / 2048);
   }
   parts = std::max<int64_t>(1, parts);
