@@ -290,7 +290,7 @@ void vec_add_and_dot_dev(Ctx &c, int slot, double *w, double sign, const double 
 double *slot_ptr(Ctx &c, int slot);
 // batched classical Gram-Schmidt pass: slot0+m <- v_m . w (m < k) ; then w -= sum_m slot[m] v_m, slot_norm <- w . w
 void vec_multi_dot_dev(Ctx &c, int slot0, const VecList &V, int k, const double *w, int64_t n);
-void vec_multi_axpy_norm_dev(Ctx &c, int slot_norm, const VecList &V, int k, int slot_coef, double *w, int64_t n);
+void vec_multi_axpy_norm_dev(Ctx &c, int slot_norm, const VecList &V, int k, int slot_coef, double *w, int64_t n, bool reduce = true);   // reduce: sum the norm over ranks
 // ---- device-driven inner FGMRES (SolverFGMRES on one block; deal.II's recurrences restated on the device) ----
 // Recurrence state of one solve in device memory.  Instead of deal.II's Householder least-squares solve of the whole
 // Hessenberg matrix in every iteration, the columns are reduced by Givens rotations as they arrive: the residual of the
@@ -307,7 +307,8 @@ FgDev *fg_state(Ctx &c);   // allocates the state + record on first use
 void fg_begin(Ctx &c, const double *beta2, double tol, int max_it, int it0);
 // column j of the cycle: mode 0 = coefficients slots[0..j] + square norm slots[j+1] (modified Gram-Schmidt chain);
 // 1 = first classical pass (slots[0..j], slots[64]), asks for a second pass after heavy cancellation; 2 = that second
-// pass (adds slots[32..], norm slots[65]); 3 = two passes done up front
+// pass (adds slots[32..], norm slots[65]); 3 = two passes done up front; 4 = as 1 with the square norm from Pythagoras:
+// slots[j+1] = |w|^2 before the update came with the coefficients in one reduction (partitioned runs)
 void fg_step(Ctx &c, const double *slots, int j, int mode);
 bool vec_multi_axpy_norm_fg(Ctx &c, int slot_norm, const VecList &V, int k, int slot_coef, double *w, int64_t n, const double *slots, int j, int mode);
 FgRec fg_wait(Ctx &c);     // spins on the mapped record until the last fg_begin / fg_step has landed

@@ -216,7 +216,7 @@ __device__ void fg_step_body(FgDev *st, const double *slots, int j, int mode, Fg
   {
     double v = 0.0;
     if (lane <= j) {
-      if (mode == 0 || mode == 1) v = slots[lane];
+      if (mode == 0 || mode == 1 || mode == 4) v = slots[lane];
       else v = (mode == 2 ? st->R[j][lane] : slots[lane]) + slots[32 + lane];
     }
     col[lane] = v;
@@ -226,10 +226,13 @@ __device__ void fg_step_body(FgDev *st, const double *slots, int j, int mode, Fg
     g[lane] = lane <= j ? st->g[lane] : 0.0;
   }
   __syncwarp();
-  const double nrm2 = mode == 0 ? slots[j + 1] : (mode == 1 ? slots[64] : slots[65]);
-  if (mode == 1) {
+  double nrm2 = mode == 0 ? slots[j + 1] : (mode == 1 ? slots[64] : slots[65]);
+  if (mode == 1 || mode == 4) {
     double h2 = 0;
     for (int i = 0; i <= j; ++i) h2 += h2s[i];   // same order on every lane
+    // mode 4 (partitioned runs): |w'|^2 = |w|^2 - sum h^2 from the ONE reduction that brought the coefficients and |w|^2 = slots[j+1];
+    // exact to ~100 eps relative whenever it is accepted (the same cancellation test sends the rest to a second pass with true norms)
+    if (mode == 4) nrm2 = slots[j + 1] - h2;
     if (nrm2 < 0.01 * (nrm2 + h2)) {            // heavy cancellation: keep the first-pass coefficients, ask for a second pass
       if (lane <= j) st->R[j][lane] = col[lane];
       __syncwarp();
@@ -556,12 +559,12 @@ void vec_multi_dot_dev(Ctx &c, int slot0, const VecList &V, int k, const double 
   LAUNCHED(c);
   allreduce_slots(c, slot0, k);
 }
-void vec_multi_axpy_norm_dev(Ctx &c, int slot_norm, const VecList &V, int k, int slot_coef, double *w, int64_t n) {
+void vec_multi_axpy_norm_dev(Ctx &c, int slot_norm, const VecList &V, int k, int slot_coef, double *w, int64_t n, bool reduce) {
   ensure_red(c);
   if (wide_ok(V, k, w, n)) k_multi_axpy_norm2<<<wide_grid(c, n), DT, 0, c.stream>>>(V, k, slot_ptr(c, slot_coef), w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot_norm), FgFuse{nullptr, nullptr, 0, 0, nullptr, 0});
   else k_multi_axpy_norm<<<vgrid(c, n), VT, 0, c.stream>>>(V, k, slot_ptr(c, slot_coef), w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot_norm));
   LAUNCHED(c);
-  allreduce_slots(c, slot_norm, 1);
+  if (reduce) allreduce_slots(c, slot_norm, 1);
 }
 
 static void ensure_red(Ctx &c) {

@@ -257,6 +257,15 @@ void solver_fgmres_dev(Ctx &c, Control &ctl, const DOp &A, double *x, const doub
         vec_dot_dev(c, slot0, aux, v(0), n);
         for (int i = 1; i <= j; ++i) vec_add_and_dot_dev(c, slot0 + i, aux, -1.0, slot_ptr(c, slot0 + i - 1), v(i - 1), v(i), n);
         vec_add_and_dot_dev(c, slot0 + j + 1, aux, -1.0, slot_ptr(c, slot0 + j), v(j), aux, n);
+      } else if (mode1 == 1 && c.comm) {
+        // partitioned: ONE reduction per iteration -- the vector itself rides along as the last "basis vector", so that |w|^2 arrives
+        // with the coefficients and the norm after the update follows from Pythagoras (k_fg_step mode 4)
+        VecList V2 = V;
+        V2.v[j + 1] = aux;
+        vec_multi_dot_dev(c, slot0, V2, j + 2, aux, n);
+        vec_multi_axpy_norm_dev(c, slot0 + 64, V, j + 1, slot0, aux, n, false);
+        fg_step(c, slots, j, 4);
+        stepped = true;
       } else if (mode1 == 1) {
         vec_multi_dot_dev(c, slot0, V, j + 1, aux, n);
         stepped = vec_multi_axpy_norm_fg(c, slot0 + 64, V, j + 1, slot0, aux, n, slots, j, 1);   // step folded into the norm kernel's last CTA

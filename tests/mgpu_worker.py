@@ -31,11 +31,12 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     elem = sys.argv[1] if len(sys.argv) > 1 else "quad"
     prec = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    defaults = len(sys.argv) > 3 and sys.argv[3] == "defaults"   # the library's default kernels / orders instead of the parity configuration
     g = N.Disc.generate(24, 10, nranks=world) if elem == "quad" else N.Disc.generate(18, 8, triangles=True, nranks=world)
     l = g.local(rank)
     ids = [N.Device.new_comm_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
-    dev = N.Device(l, device_id=local_rank, ordering=0, ortho=0, comm_id=ids[0])
+    dev = N.Device(l, device_id=local_rank, comm_id=ids[0], block_rows=128) if defaults else N.Device(l, device_id=local_rank, ordering=0, ortho=0, comm_id=ids[0])
     nu = 0.1
     sol = N.synthetic_state(g, 7, noise=1e-4)
     dev.upload(N.VEC_SOLUTION, l.scatter_owned(sol, g.n_u))
@@ -45,7 +46,9 @@ def main():
     gu, gp = dev.download_ghosts(N.VEC_SOLUTION)
     l2gu, l2gp = l.array("L2G_U"), l.array("L2G_P")
     assert np.array_equal(gu, sol[l2gu[l.n_u_owned:]]) and np.array_equal(gp, sol[g.n_u + l2gp[l.n_p_owned:]])
-    r_d = dev.assemble(N.MODE_NEWTON, True, nu)
+    mode = N.MODE_STOKES if defaults else N.MODE_NEWTON   # defaults: the Stokes branch, whose node view of F is the multi-rank path to cover
+    r_d = dev.assemble(mode, True, nu)
+    view = dev.view()
     # block product on the assembled matrices
     x = np.random.default_rng(3).uniform(-1, 1, g.n_u + g.n_p)
     dev.upload(N.VEC_TMP0, l.scatter_owned(x, g.n_u))
@@ -56,14 +59,14 @@ def main():
     x_d = gather_global(l, g, dev.download(N.VEC_DELTA))
     dev.save_eval_point()
     dev.update(1.0)
-    r2_d = dev.assemble(N.MODE_NEWTON, False, nu)
+    r2_d = dev.assemble(mode, False, nu)
     drag_d, lift_d = dev.lift_drag(nu)
     stats = (dev.stat("HALO_EXCHANGES"), dev.stat("ALLREDUCES"))
     if rank == 0:
         o = N.Oracle(g)
         o.vec(0)[:] = sol
         o.vec(2)[:] = 0
-        r_o = o.assemble(N.MODE_NEWTON, True, nu)
+        r_o = o.assemble(mode, True, nu)
         assert abs(r_d - r_o) <= 1e-11 * r_o, (r_d, r_o)
         assert np.abs(res_d - o.vec(3)).max() <= 1e-11 * np.abs(o.vec(3)).max()
         y_o = o.spmv(N.BLOCK_J, x)
@@ -73,12 +76,14 @@ def main():
         x_o = o.vec(2).copy()
         assert np.linalg.norm(x_d - x_o) <= 1e-8 * np.linalg.norm(x_o), np.linalg.norm(x_d - x_o) / np.linalg.norm(x_o)
         o.vec(0)[:] = sol + x_o
-        r2_o = o.assemble(N.MODE_NEWTON, False, nu)
+        r2_o = o.assemble(mode, False, nu)
         assert abs(r2_d - r2_o) <= 1e-6 * max(r2_o, 1e-6), (r2_d, r2_o)
         drag_o, lift_o = o.lift_drag(nu)
         assert abs(drag_d - drag_o) <= 1e-6 * abs(drag_o) and abs(lift_d - lift_o) <= 1e-6 * max(abs(lift_o), abs(drag_o))
-        print(f"MGPU_WORKER_OK world {world} elem {elem} prec {prec}: outer iterations gpu {it_d} / oracle {it_o}, halo exchanges {stats[0]}, "
-              f"allreduces {stats[1]}")
+        if defaults:
+            assert view == 2, view   # F = K (x) I_2: the node view with ghost pairs and the node-layout ghost import
+        print(f"MGPU_WORKER_OK world {world} elem {elem} prec {prec}{' defaults (view ' + str(view) + ')' if defaults else ''}: outer iterations gpu {it_d} / oracle {it_o}, "
+              f"halo exchanges {stats[0]}, allreduces {stats[1]}")
     dist.barrier()
     dev.close()
     dist.destroy_process_group()

@@ -22,13 +22,27 @@ def test_two_gpu_run_matches_global_oracle(elem, prec):
     B (diag(F)^-1 (Bt x)) with two ghost imports in the CG solve."""
     if _ngpus() < 2:
         pytest.skip("needs two GPUs")
+    _run_worker(elem, prec)
+
+
+@pytest.mark.parametrize("elem,prec", [("quad", 0), ("tri", 2)])
+def test_two_gpu_run_with_library_defaults(elem, prec):
+    """The same two-rank runs with the library's defaults (CTA-local sweep blocks, node view of F in the Stokes branch with ghost
+    pairs and the node-layout ghost import, device-driven inner FGMRES with one reduction per iteration) against the global oracle in
+    its natural order: another preconditioner, the same converged increment (1e-8), residual and forces."""
+    if _ngpus() < 2:
+        pytest.skip("needs two GPUs")
+    _run_worker(elem, prec, "defaults")
+
+
+def _run_worker(elem, prec, *extra):
     worker = os.path.join(N.ROOT, "tests", "mgpu_worker.py")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29741", worker, elem, str(prec)], capture_output=True, text=True, timeout=150)
+                        "--master-port", "29741", worker, elem, str(prec), *extra], capture_output=True, text=True, timeout=200)
     print(r.stdout[-2000:])
     logdir = os.path.join(N.ROOT, "gpurun_out")
     if os.path.isdir(logdir):
-        with open(os.path.join(logdir, f"mgpu_{elem}_{prec}.log"), "w") as f:
+        with open(os.path.join(logdir, f"mgpu_{elem}_{prec}{'_' + extra[0] if extra else ''}.log"), "w") as f:
             f.write(r.stdout + "\n---- stderr ----\n" + r.stderr)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MGPU_WORKER_OK" in r.stdout
