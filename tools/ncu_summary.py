@@ -99,15 +99,20 @@ def traffic(path, mesh, ordering):
     for r in body:
         b = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
         per[short(r[idx["Kernel Name"]])].append(b)
-    names = {"sgs_F": "k_sweep_block", "spmv_F": "k_spmv_tma", "block_spmv": "k_spmv_tma"}
+    # k_spmv_tma<1, 0> = general rows (the Jacobian block product; also the F product when no node view is active),
+    # k_spmv_tma<1, 1|2> = node rows (the F product of the inner solves in the Stokes-type branches)
+    node = [v for k, vs in per.items() if k.startswith("k_spmv_tma<1, 1") or k.startswith("k_spmv_tma<1, 2") for v in vs]
+    general = [v for k, vs in per.items() if k.startswith("k_spmv_tma<1, 0") for v in vs]
+    sweep = [v for k, vs in per.items() if k.startswith("k_sweep_block") for v in vs]
+    med = lambda v: sorted(v)[len(v) // 2]
     res = {}
-    for key, pat in names.items():
-        vals = [v for k, vs in per.items() if k.startswith(pat) for v in vs]
-        if not vals:
-            continue
-        # the Jacobian block product is the largest launch of the SpMV kernel, the F product of the inner solves the most frequent one
-        res[key] = max(vals) if key == "block_spmv" else sorted(vals)[len(vals) // 2]
-    print(json.dumps({"mesh": mesh, "ordering": int(ordering), "source": path.split("/")[-1], "how": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum per launch (median over the captured launches; block_spmv = the largest SpMV launch)",
+    if sweep:
+        res["sgs_F"] = med(sweep)
+    if node or general:
+        res["spmv_F"] = med(node) if node else med(general)
+    if general and node:
+        res["block_spmv"] = max(general)
+    print(json.dumps({"mesh": mesh, "ordering": int(ordering), "source": path.split("/")[-1], "how": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum per launch (median over the captured launches; block_spmv = the largest launch on general rows, when one was captured)",
                       "bytes_per_launch": res, "all_kernels_median_bytes": {k: sorted(v)[len(v) // 2] for k, v in per.items()}}, indent=1))
 
 
