@@ -492,9 +492,9 @@ def main():
     dev.set_time_params(B.MODE_NEWTON, 1.0 / 90.0)
     gstate = B.synthetic_state(g, 1234)
     dev.upload(B.VEC_SOLUTION, d.scatter_owned(gstate, g.n_u) if world > 1 else gstate)
-    names = [("block_spmv", 0), ("spmv_F", 1), ("assembly_newton", 2), ("dot", 3), ("axpy", 4), ("sgs_F", 5), ("ilu_apply_F", 6), ("ilu_factor_F", 7)]
-    if world > 1:
-        names = [x for x in names if x[1] in (2, 3, 4, 5, 6, 7)] + [("block_spmv", 0), ("spmv_F", 1)]   # collective ones last, all ranks alike
+    # the matrix kernels first, on the matrices of the last step (the views of F follow the VALUES: DESIGN.md section 3); the assembly
+    # timing, which overwrites them with a Newton-branch matrix, last.  Same order on every rank (the SpMVs import ghosts).
+    names = [("block_spmv", 0), ("spmv_F", 1), ("sgs_F", 5), ("ilu_apply_F", 6), ("ilu_factor_F", 7), ("dot", 3), ("axpy", 4), ("assembly_newton", 2)]
     for _, w in names:
         dev.time_kernel(w, 5, True)
     k_ms = {name: dev.time_kernel(w, reps, True) for name, w in names}
