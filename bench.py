@@ -194,7 +194,7 @@ def run_reference(args, emit):
               f"({smp['t_asm']:.2f} s each) + solve " +
               (f"run to convergence ({smp['outer_done']} outer iterations, {smp['t_solve']:.2f} s)" if not extrapolated else
                f"capped at {smp['outer_done']} outer iterations ({smp['t_solve']:.2f} s measured), extrapolated linearly to {total or smp['outer_done']} outer iterations "
-               f"({'the count of the oracle`s own full solve, profiles/oracle_full_solves.json' if fixture and not args.cpu_outer_total else '--cpu-outer-total' if args.cpu_outer_total else 'no full count known: NOT extrapolated'})"))
+               f"({(fixture.get('source') or 'the count of the oracle`s own full solve') + ', profiles/oracle_full_solves.json' if fixture and not args.cpu_outer_total else '--cpu-outer-total' if args.cpu_outer_total else 'no full count known: NOT extrapolated'})"))
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": val * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference", "extrapolated": extrapolated,
@@ -594,7 +594,7 @@ def main():
         smp = CpuSampler(nx, ny, args.solver, args.prec, args.tol, nu).sample(args.cpu_outer_cap, target_s=args.cpu_sample_s)
         fixture = outer_total_fixture(args.mesh, args.solver, args.prec)
         total = args.cpu_outer_total or (fixture["outer"] if fixture else stats["outer"])
-        src = "--cpu-outer-total" if args.cpu_outer_total else ("the oracle's own full solve (profiles/oracle_full_solves.json)" if fixture else "this run's GPU solve")
+        src = "--cpu-outer-total" if args.cpu_outer_total else ((fixture.get("source") or "the oracle's own full solve") + " (profiles/oracle_full_solves.json)" if fixture else "this run's GPU solve")
         extrapolated = not smp["converged"]
         scale = max(1.0, total / smp["outer_done"]) if extrapolated else 1.0
         cpu_val = 2 * smp["t_asm"] + smp["t_solve"] * scale

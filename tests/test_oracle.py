@@ -219,6 +219,47 @@ def test_inner_preconditioners_by_definition(prob):
         np.testing.assert_allclose(o.inner_apply(blk, 1, x), y, rtol=1e-8, atol=1e-11 * np.abs(y).max())
 
 
+def test_inner_preconditioners_on_arbitrary_blocks_and_orders(prob):
+    """orc_set_blocks: any set of blocks with any elimination sequence (what the device's block-local sweeps use).  SGS and ILU(0)
+    then equal the dense definitions on the permuted matrix with the couplings between blocks dropped; nb = 0 restores Ifpack's
+    contiguous ranges in natural order."""
+    d, o = prob
+    o.vec(0)[:] = N.synthetic_state(d, 8)
+    o.assemble(N.MODE_NEWTON, False, 0.05)
+    rng = np.random.default_rng(5)
+    for which, blk in ((0, N.BLOCK_F), (1, N.BLOCK_MP)):
+        A = o.csr(blk).toarray()
+        n = A.shape[0]
+        nb = 5
+        owner = rng.integers(0, nb, n)
+        order = np.concatenate([rng.permutation(np.nonzero(owner == b)[0]) for b in range(nb)]).astype(np.int32)
+        off = np.concatenate([[0], np.cumsum(np.bincount(owner, minlength=nb))]).astype(np.int64)
+        o.set_blocks(which, off, order)
+        try:
+            Ab = A * (owner[:, None] == owner[None, :])
+            Ap = Ab[np.ix_(order, order)]
+            x = rng.normal(size=n)
+            D, L, U = np.diag(np.diag(Ap)), np.tril(Ap, -1), np.triu(Ap, 1)
+            ref = np.empty(n)
+            ref[order] = np.linalg.solve(D + U, D @ np.linalg.solve(D + L, x[order]))
+            np.testing.assert_allclose(o.inner_apply(blk, 0, x), ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max())
+            pat = Ap != 0
+            LU = Ap.copy()
+            for i in range(n):
+                for k in np.nonzero(pat[i, :i])[0]:
+                    LU[i, k] /= LU[k, k]
+                    js = np.nonzero(pat[i, k + 1:] & pat[k, k + 1:])[0] + k + 1
+                    LU[i, js] -= LU[i, k] * LU[k, js]
+            ref[order] = np.linalg.solve(np.triu(LU), np.linalg.solve(np.tril(LU, -1) + np.eye(n), x[order]))
+            np.testing.assert_allclose(o.inner_apply(blk, 1, x), ref, rtol=1e-8, atol=1e-11 * np.abs(ref).max())
+        finally:
+            o.set_blocks(which)
+        # back to the contiguous ranges: the natural-order result again
+        Dn, Ln, Un = np.diag(np.diag(A)), np.tril(A, -1), np.triu(A, 1)
+        np.testing.assert_allclose(o.inner_apply(blk, 0, x), np.linalg.solve(Dn + Un, Dn @ np.linalg.solve(Dn + Ln, x)), rtol=1e-9,
+                                   atol=1e-12 * np.abs(x).max())
+
+
 def test_schur_complement_product(prob):
     d, o = prob
     o.vec(0)[:] = N.synthetic_state(d, 9)
