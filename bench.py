@@ -110,8 +110,12 @@ class CpuSampler:
     def __init__(self, nx, ny, solver, prec, tol, nu, threads=None):
         from navier_stokes_solver_b200 import binding as B
         from oracle.pyoracle import Oracle, orc
-        if threads:
-            orc().orc_set_threads(threads)
+        if not threads:
+            # one rank per ~20 000 unknowns at least, as nobody runs a 3 k-DoF mesh on 16 MPI ranks (and OpenMP regions over a few
+            # thousand entries cost more to start than to run)
+            probe = B.Disc.generate(nx, ny)
+            threads = int(max(1, min(int(orc().orc_get_threads()), probe.n // 20000)))
+        orc().orc_set_threads(threads)
         self.threads = int(orc().orc_get_threads())
         self.o = Oracle(B.Disc.generate(nx, ny, nranks=self.threads))
         self.solver, self.prec, self.tol, self.nu = solver, prec, tol, nu

@@ -302,7 +302,22 @@ struct FgFuse { FgDev *st; const double *slots; int j, mode; FgRec *rec; long lo
 // loads of a step in flight together.  One or two steps per thread, one reduction per chunk, 2 x #SMs CTAs of 512 threads.
 constexpr int DT = 512, KC = 8;
 
-__global__ void __launch_bounds__(DT, 2) k_multi_dot2(VecList V, int k, const double *__restrict__ w, int64_t n, double *partial, unsigned int *counter, double *result) {
+// The Krylov basis is re-read by every Gram-Schmidt pass of a restart cycle (up to 30 x 4.3 MB at the README size, about the size of
+// the 126 MB L2): its loads ask the L2 to keep the lines (evict-last), while the matrix streams of the SpMV and the sweeps pass
+// through evict-first (tma.cuh).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double2 ld_keep(const double2 *p, uint64_t policy) {
+  double2 v;
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy));
+  return v;
+}
+
+__global__ void __launch_bounds__(DT, 2) k_multi_dot2(VecList V, int k, const double *__restrict__ w, int64_t n, double *partial, unsigned int *counter, double *result,
+                                                      int keep_basis) {
   __shared__ const double *sv[32];
   __shared__ double sh[DT / 32][KC];
   __shared__ bool last;
@@ -311,6 +326,7 @@ __global__ void __launch_bounds__(DT, 2) k_multi_dot2(VecList V, int k, const do
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const int64_t n2 = n >> 1;
   const double2 *w2 = reinterpret_cast<const double2 *>(w);
+  const uint64_t keep = l2_policy_evict_last();
   for (int c0 = 0; c0 < k; c0 += KC) {
     const int kc = min(KC, k - c0);
     double acc[KC];
@@ -320,7 +336,7 @@ __global__ void __launch_bounds__(DT, 2) k_multi_dot2(VecList V, int k, const do
       const double2 wv = w2[i];
       double2 vv[KC];
 #pragma unroll
-      for (int m = 0; m < KC; ++m) vv[m] = m < kc ? reinterpret_cast<const double2 *>(sv[c0 + m])[i] : make_double2(0.0, 0.0);
+      for (int m = 0; m < KC; ++m) vv[m] = m < kc ? (keep_basis ? ld_keep(reinterpret_cast<const double2 *>(sv[c0 + m]) + i, keep) : reinterpret_cast<const double2 *>(sv[c0 + m])[i]) : make_double2(0.0, 0.0);
 #pragma unroll
       for (int m = 0; m < KC; ++m) acc[m] = fma(wv.y, vv[m].y, fma(wv.x, vv[m].x, acc[m]));
     }
@@ -361,7 +377,7 @@ __global__ void __launch_bounds__(DT, 2) k_multi_dot2(VecList V, int k, const do
 }
 
 __global__ void __launch_bounds__(DT, 2) k_multi_axpy_norm2(VecList V, int k, const double *coef, double *__restrict__ w, int64_t n, double *partial,
-                                                         unsigned int *counter, double *norm2, FgFuse fuse) {
+                                                         unsigned int *counter, double *norm2, FgFuse fuse, int keep_basis) {
   __shared__ const double *sv[32];
   __shared__ double sc[32];
   __shared__ double sh[DT / 32];
@@ -370,13 +386,14 @@ __global__ void __launch_bounds__(DT, 2) k_multi_axpy_norm2(VecList V, int k, co
   __syncthreads();
   const int64_t n2 = n >> 1;
   double2 *w2 = reinterpret_cast<double2 *>(w);
+  const uint64_t keep = l2_policy_evict_last();
   double acc = 0;
   for (int64_t i = blockIdx.x * (int64_t)DT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * DT) {
     double2 wv = w2[i];
     for (int m0 = 0; m0 < k; m0 += KC) {
       double2 vv[KC];
 #pragma unroll
-      for (int m = 0; m < KC; ++m) vv[m] = m0 + m < k ? reinterpret_cast<const double2 *>(sv[m0 + m])[i] : make_double2(0.0, 0.0);
+      for (int m = 0; m < KC; ++m) vv[m] = m0 + m < k ? (keep_basis ? ld_keep(reinterpret_cast<const double2 *>(sv[m0 + m]) + i, keep) : reinterpret_cast<const double2 *>(sv[m0 + m])[i]) : make_double2(0.0, 0.0);
 #pragma unroll
       for (int m = 0; m < KC; ++m) {   // coefficients beyond k are zero: same order of subtractions as the narrow kernel
         const double cm = sc[(m0 + m) & 31];
@@ -487,7 +504,7 @@ bool vec_multi_axpy_norm_fg(Ctx &c, int slot_norm, const VecList &V, int k, int 
   if (c.comm || !wide_ok(V, k, w, n)) { vec_multi_axpy_norm_dev(c, slot_norm, V, k, slot_coef, w, n); return false; }
   FgDev *st = fg_state(c);
   k_multi_axpy_norm2<<<wide_grid(c, n), DT, 0, c.stream>>>(V, k, slot_ptr(c, slot_coef), w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot_norm),
-                                                          FgFuse{st, slots, j, mode, (FgRec *)c.fg_rec, ++c.fg_seq});
+                                                          FgFuse{st, slots, j, mode, (FgRec *)c.fg_rec, ++c.fg_seq}, c.l2_hints ? 1 : 0);
   LAUNCHED(c);
   return true;
 }
@@ -554,14 +571,14 @@ double *slot_ptr(Ctx &c, int slot) { ensure_red(c); return c.red_result.p + slot
 void vec_multi_dot_dev(Ctx &c, int slot0, const VecList &V, int k, const double *w, int64_t n) {
   ensure_red(c);
   if (k < 1 || k > 31) throw std::invalid_argument("multi-dot handles 1..31 vectors");
-  if (wide_ok(V, k, w, n)) k_multi_dot2<<<wide_grid(c, n), DT, 0, c.stream>>>(V, k, w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot0));
+  if (wide_ok(V, k, w, n)) k_multi_dot2<<<wide_grid(c, n), DT, 0, c.stream>>>(V, k, w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot0), c.l2_hints ? 1 : 0);
   else k_multi_dot<<<vgrid(c, n), VT, 0, c.stream>>>(V, k, w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot0));
   LAUNCHED(c);
   allreduce_slots(c, slot0, k);
 }
 void vec_multi_axpy_norm_dev(Ctx &c, int slot_norm, const VecList &V, int k, int slot_coef, double *w, int64_t n, bool reduce) {
   ensure_red(c);
-  if (wide_ok(V, k, w, n)) k_multi_axpy_norm2<<<wide_grid(c, n), DT, 0, c.stream>>>(V, k, slot_ptr(c, slot_coef), w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot_norm), FgFuse{nullptr, nullptr, 0, 0, nullptr, 0});
+  if (wide_ok(V, k, w, n)) k_multi_axpy_norm2<<<wide_grid(c, n), DT, 0, c.stream>>>(V, k, slot_ptr(c, slot_coef), w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot_norm), FgFuse{nullptr, nullptr, 0, 0, nullptr, 0}, c.l2_hints ? 1 : 0);
   else k_multi_axpy_norm<<<vgrid(c, n), VT, 0, c.stream>>>(V, k, slot_ptr(c, slot_coef), w, n, c.red_partial.p, c.red_counter.p, slot_ptr(c, slot_norm));
   LAUNCHED(c);
   if (reduce) allreduce_slots(c, slot_norm, 1);

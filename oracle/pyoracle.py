@@ -23,6 +23,9 @@ def orc():
     if _orc is None:
         if not os.path.exists(LIBORC):
             raise RuntimeError(f"{LIBORC} is missing: run `make -C oracle`")
+        # OpenMP threads that sleep instead of spinning at barriers: a loaded host (other jobs, more threads than free cores) then
+        # costs the oracle a little instead of orders of magnitude (read by libgomp when it is first loaded)
+        os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
         L = C.CDLL(LIBORC)
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
