@@ -5,8 +5,12 @@
 //   the inner SolverFGMRES / SolverCG on single blocks (I4), and the preconditioner classes
 //   PreconditionBlockDiagonal / BlockTriangular / aSIMPLE in both flavours
 //   (NSSolverStationary.hpp:115-335, NSSolver.hpp:138-384).
-// The iteration logic (what deal.II's solvers do step by step, default AdditionalData) runs on the
-// host; every vector lives on the device and all arithmetic on vectors is a CUDA kernel.
+// The iteration logic of the OUTER solvers (what deal.II's solvers do step by step, default AdditionalData) runs on the
+// host; every vector lives on the device and all arithmetic on vectors is a CUDA kernel.  The INNER FGMRES solves on F --
+// a couple of hundred thousand iterations per Newton step of the README run -- keep their recurrences on the device
+// (solver_fgmres_dev): Hessenberg column, Givens rotations, residual estimate and SolverControl::check run in k_fg_step (or in
+// the last CTA of the norm kernel), the host polls a mapped record instead of synchronising the stream, and the next
+// iteration's sweep is queued behind the verdict and skips itself if the solve is over.
 // Orthogonalisation of GMRES / FGMRES (NSX_OPT_ORTHO): 0 = deal.II's modified Gram-Schmidt as a chain of fused
 // add_and_dot kernels that hand their coefficients on in device memory; 1 = two passes of batched classical
 // Gram-Schmidt (all dot products of a pass in one launch, all updates + the norm in another); 2 (default) = as 1 for

@@ -5,10 +5,10 @@
 // preconditioners with overlap 0: each MPI rank factors and sweeps its own diagonal block and drops every coupling to
 // another rank.  Elimination order 2 (NSX_OPT_ORDERING, the default) gives the GPU the same structure at the granularity
 // it needs: the owned rows are cut into spatially compact blocks (weighted recursive coordinate bisection of the dof
-// positions, one block per SM at the README size -- what `mpirun -n 148` with a geometric partitioner would produce) and
-// ONE CTA owns a block for the whole application:
-//   * the block's slice of the work vector (<= 8192 rows = 64 KB) lives in shared memory, so the dependent gathers of a
-//     sweep never leave the SM and a dependency level costs one __syncthreads instead of a grid-wide barrier;
+// positions, two blocks per SM at the README size -- what `mpirun -n 296` with a geometric partitioner would produce) and
+// ONE CTA owns a block for the whole application (two CTAs are resident per SM and hide each other's level latency):
+//   * the block's slice of the work vector (<= 4096 rows) lives in shared memory, so the dependent gathers of a sweep never
+//     leave the SM and a dependency level costs one named barrier among 16 warps instead of a grid-wide barrier;
 //   * rows inside a block follow a multicolour order re-sorted by dependency level (32 levels for Q3/Q2); a level is one
 //     or a few "passes" of up to 512 lanes, a row owning ceil(entries / Q) consecutive lanes of a warp (Q = 4 entries per
 //     lane), reduced by a segmented shuffle reduction; only the end of a level costs a barrier, and only among the 16
@@ -20,6 +20,9 @@
 //     frees each region are fixed by the host when the plan is built.  The lower sweep streams the strictly lower
 //     entries, the upper sweep the strictly upper ones: every stored non-zero of the block-diagonal part crosses HBM
 //     exactly once per application.
+//   * NODE = true (decouple.cu): the rows are velocity nodes of F = K (x) I_2; one matrix value serves the (x, y) pair of a node, the
+//     work vector holds a double2 per row, and the vector entries of a pair come from two index arrays (reference or node layout).
+// Elimination order 3 keeps the blocks and takes Ifpack's natural order inside (many short levels; the stronger ILU(0)).
 // The reciprocal of the diagonal is stored (one rounding away from the division the CPU oracle does).
 #include <algorithm>
 #include <numeric>
@@ -48,7 +51,7 @@ constexpr size_t SMEM_PER_CTA = (size_t)(227 * 1024 / BLOCKS_PER_SM - 1024) / 12
 //                    {T | Q << 16, rows | rounds << 16 | flags << 24, value count, index count}; flags: 1 upper sweep, 2 level ends
 struct PassHdr { int val_off, idx_off, ring16, wait; int tq, rrf, val_cnt, idx_cnt; };
 
-// NODE: a row is a velocity node and stands for the vector entries (2 row, 2 row + 1); one matrix value serves both components
+// NODE: a row is a velocity node and stands for the vector entries perm[row] (x) and perm_y[row] (y); one matrix value serves both
 template <bool SGS, bool NODE>
 __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_sweep_block(const BlkDesc *__restrict__ blks, const PassHdr *__restrict__ passes, const double *__restrict__ bl_val,
                                                         const uint16_t *__restrict__ bl_idx, const int32_t *__restrict__ perm, const int32_t *__restrict__ perm_y,
@@ -275,7 +278,9 @@ int geometric_blocks(Ctx &c, int block, const std::vector<int64_t> &rowptr, int6
     // the block-Jacobi preconditioner) does not grow faster than the machine
     const int per_sm = c.nranks > 1 ? 1 : BLOCKS_PER_SM;
     const int64_t slots = (int64_t)std::max(1, c.num_sms) * per_sm, per = n / slots;
-    if (per <= 256) parts = std::min<int64_t>(slots, (n + 128) / 256);
+    // (no block below 512 rows: the unsteady aSIMPLE's single ILU(0) application per iteration on the reference's mesh -- 52 k
+    // velocity nodes -- converges under the reference's iteration cap with 102 blocks of 512 nodes and misses it with 203 of 256)
+    if (per <= 512) parts = std::min<int64_t>(slots, (n + 256) / 512);
     else parts = slots * ((per + 2047) / 2048);
   }
   parts = std::max<int64_t>(1, parts);
