@@ -56,6 +56,10 @@ enum nsx_option {
                              (orderings 2 and 3); 0: always the full pattern */
   NSX_OPT_L2_HINTS = 8,   /* 1 (default): the TMA copies of matrix values / columns carry an evict-first L2 policy, so that the streams
                              (read once per launch) do not push the Krylov basis out of the 126 MB L2; 0: no hint */
+  NSX_OPT_PRECOND_LAG = 9, /* n > 0: the numeric preconditioner data (ILU(0) factors, Gauss-Seidel values, AMG hierarchy, Schur
+                             complement) built in one solve also serve the next n solves -- Newton iterations / line-search states
+                             change the matrices little, and FGMRES tolerates a lagged preconditioner; 0 (default): every solve
+                             rebuilds them, as the initialize() calls of the reference do (NSSolverStationary.cpp:583,601,621) */
   NSX_OPT_HOST_INNER = 6  /* 1: the inner FGMRES solves run their recurrences on the host (one stream synchronisation per
                              iteration, round-1 behaviour); 0 (default): device-side Givens / convergence decision, the host
                              polls a mapped record and launches the next sweep speculatively */
@@ -65,6 +69,7 @@ enum nsx_stat {
   NSX_STAT_LEVELS_F = 4, NSX_STAT_LEVELS_MP = 5, NSX_STAT_LEVELS_S = 6, NSX_STAT_SPMV_CALLS = 7,
   NSX_STAT_ASSEMBLY_COLOURS = 8, NSX_STAT_ASSEMBLY_TABLES = 9, NSX_STAT_LAST_STEP = 10,
   NSX_STAT_HALO_EXCHANGES = 11, NSX_STAT_ALLREDUCES = 12,
+  NSX_STAT_PRECOND_BUILDS = 16, /* numeric preconditioner builds since nsx_create (see NSX_OPT_PRECOND_LAG) */
   NSX_STAT_SWEEP_BYTES_F = 14, NSX_STAT_SPMV_BYTES_F = 15, /* stored bytes per launch of the F sweeps / the inner solves' F product */
   NSX_STAT_F_DECOUPLED = 13 /* view found by the last check of NSX_OPT_DECOUPLE: 0 full, 1 same-component, 2 nodes */
 };

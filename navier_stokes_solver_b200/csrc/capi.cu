@@ -132,7 +132,7 @@ int nsx_set_option(nsx_ctx *ctx, int option, int64_t value) {
         ctx->ordering = (int)value; ctx->ordering_auto = false; break;
       case NSX_OPT_BLOCK_ROWS:
         if (value < 0 || value > 4096) throw std::invalid_argument("block rows must lie in [0, 4096] (0: automatic)");
-        ctx->block_rows = (int)value; ctx->tri.clear(); break;
+        ctx->block_rows = (int)value; ctx->tri.clear(); ctx->schur_built_at = ctx->amg_built_at = -1; break;
       case NSX_OPT_VERBOSE: ctx->verbose = (int)value; break;
       case NSX_OPT_ORTHO:
         if (value < 0 || value > 2) throw std::invalid_argument("orthogonalisation must be 0, 1 or 2");
@@ -145,6 +145,9 @@ int nsx_set_option(nsx_ctx *ctx, int option, int64_t value) {
         ctx->stream_spmv = (int)value; break;
       case NSX_OPT_HOST_INNER: ctx->host_inner = value != 0; break;
       case NSX_OPT_L2_HINTS: ctx->l2_hints = value != 0; break;
+      case NSX_OPT_PRECOND_LAG:
+        if (value < 0 || value > 1000000) throw std::invalid_argument("preconditioner lag must be a solve count >= 0");
+        ctx->precond_lag = (int)value; break;
       case NSX_OPT_DECOUPLE:
         if (value < 0 || value > 2) throw std::invalid_argument("decouple must be 0 (off), 1 (same-component view) or 2 (node view where it holds)");
         ctx->decouple = value != 0; ctx->decouple_nodes = value == 2; ctx->dec_epoch = 0; break;
@@ -174,6 +177,7 @@ int64_t nsx_get_stat(const nsx_ctx *ctx, int stat) {
     case NSX_STAT_LAST_STEP: return ctx->last_step;
     case NSX_STAT_HALO_EXCHANGES: return ctx->stat_halo;
     case NSX_STAT_ALLREDUCES: return ctx->stat_allreduce;
+    case NSX_STAT_PRECOND_BUILDS: return ctx->stat_precond_builds;
     case NSX_STAT_SWEEP_BYTES_F: {   // stored bytes one application of the F sweeps streams: the plan of the view found by the last check
       int view = (ctx->dec_epoch == ctx->matrix_epoch && ctx->dec_ok) ? (ctx->node_ok ? 2 : 1) : 0;
       if (view == 2 && (ctx->ordering < 2 || ctx->stream_spmv != 3)) view = 1;
@@ -214,7 +218,7 @@ int nsx_set_discretisation(nsx_ctx *ctx, int elem, int64_t n_cells, const double
     for (auto &v : c.vec) { v.alloc(c.nvec); v.zero(c.stream); }
     c.owned_u = {0, n_u}; c.owned_p = {0, n_p};
     c.have_disc = true; c.finalized = false; c.S_symbolic = false;
-    c.tri.clear();
+    c.tri.clear(); c.schur_built_at = c.amg_built_at = -1;
     NSX_CUDA(cudaStreamSynchronize(c.stream));
   });
 }
@@ -235,7 +239,7 @@ int nsx_set_pattern(nsx_ctx *ctx, int block, int64_t nrows, int64_t ncols, const
       c.F_cross.release(); c.Fd = DevCSR(); c.Kn = DevCSR(); c.node_struct = 0; c.h_comp_u.clear(); c.dec_epoch = 0;
     }
     c.matrix_epoch++;
-    if (block == NSX_BLOCK_B || block == NSX_BLOCK_BT) { c.S_symbolic = false; tri_erase(c, NSX_BLOCK_S); }
+    if (block == NSX_BLOCK_B || block == NSX_BLOCK_BT) { c.S_symbolic = false; c.schur_built_at = -1; tri_erase(c, NSX_BLOCK_S); }
   });
 }
 
@@ -277,7 +281,7 @@ int nsx_set_ranks(nsx_ctx *ctx, int nranks, const int64_t *owned_u, const int64_
       if (owned_u[r + 1] < owned_u[r] || owned_p[r + 1] < owned_p[r]) throw std::invalid_argument("owned ranges must be ascending");
     c.owned_u.assign(owned_u, owned_u + nranks + 1);
     c.owned_p.assign(owned_p, owned_p + nranks + 1);
-    c.tri.clear();
+    c.tri.clear(); c.schur_built_at = c.amg_built_at = -1;
     c.finalized = false;
   });
 }
@@ -294,7 +298,7 @@ int nsx_set_partition(nsx_ctx *ctx, int64_t n_u_owned, int64_t n_p_owned) {
     c.n_ug = lu - n_u_owned; c.n_pg = lp - n_p_owned;
     c.nvec = lu + lp;
     c.owned_u = {0, c.n_u}; c.owned_p = {0, c.n_p};
-    c.tri.clear();
+    c.tri.clear(); c.schur_built_at = c.amg_built_at = -1;
     c.finalized = false;
   });
 }

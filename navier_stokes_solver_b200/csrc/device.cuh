@@ -112,6 +112,7 @@ struct TriPlan {
   DevBuf<double> val;                   // filtered values (SGS) or LU factors (ILU)
   DevBuf<double> work, yp;              // intermediate vectors (permuted numbering)
   bool factored = false;
+  long long built_at = -1;              // solve (Ctx::solve_seq) whose matrix values the numeric data hold; -1: none yet
   int coop_grid = 0;                    // grid of the cooperative sweep (0: not sized yet)
   // colour-phased persistent sweep (multicolour order): rows of a colour are contiguous in the permuted numbering
   std::vector<int64_t> cptr;            // colour pointers (empty for the natural order)
@@ -159,6 +160,10 @@ struct Ctx {
   int verbose = 0;
   int ordering = 2;      // ILU / SGS elimination order: 0 natural (Ifpack), 1 multicolour over the owned range, 2 (default) multicolour inside CTA-local blocks
   bool l2_hints = true;   // NSX_OPT_L2_HINTS: TMA matrix streams carry an evict-first L2 policy
+  // NSX_OPT_PRECOND_LAG: numeric preconditioner data (ILU factors, sweep values, AMG hierarchy, Schur complement) built in solve s
+  // serve the solves s+1 .. s+lag as well (0, default: rebuilt in every solve, as the reference's initialize() calls do)
+  int precond_lag = 0;
+  long long solve_seq = 0, schur_built_at = -1, amg_built_at = -1, stat_precond_builds = 0;
   bool ordering_auto = true;   // NSX_OPT_ORDERING never set: preconditioners that are a single ILU(0) application per iteration use ordering 3
   int block_rows = 0;    // ordering 2: target rows per block (0: n / #SMs clamped to [512, 4096])
   bool host_inner = false;  // inner FGMRES recurrences on the host (round-1 behaviour) instead of the device

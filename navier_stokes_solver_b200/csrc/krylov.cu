@@ -498,25 +498,39 @@ struct Preconditioner {
     } else {
       opS = [this](double *y, const double *x) { spmv(c, c.S, x, y); };
     }
+    // numeric builds, skipped while NSX_OPT_PRECOND_LAG lets the data of an earlier solve stand in (a plan that never held values, or
+    // whose values are older than the lag, is always rebuilt)
+    auto reuse = [this](long long built_at) { return c.precond_lag > 0 && built_at >= 0 && c.solve_seq - built_at <= c.precond_lag; };
+    auto sgs_values = [&](TriPlan &P, const DevCSR &A) {
+      if (!P.factored && reuse(P.built_at)) return;   // (a plan holding LU factors of another preconditioner type does not count)
+      tri_refresh_values(c, P, A); P.built_at = c.solve_seq; c.stat_precond_builds++;
+    };
+    auto ilu = [&](TriPlan &P, const DevCSR &A) {
+      if (P.factored && reuse(P.built_at)) return;
+      ilu0_factor(c, P, A); P.built_at = c.solve_seq; c.stat_precond_builds++;
+    };
     if (type == 0) {
       // Gauss-Seidel sweeps skip exact zeros too (plan variant 1); ILU(0) needs the full pattern (fill lands on those entries)
       F = &tri_plan(c, NSX_BLOCK_F, flavour == NSX_STATIONARY ? view : ilu_variant); Mp = &tri_plan(c, NSX_BLOCK_MP);
-      if (flavour == NSX_STATIONARY) { tri_refresh_values(c, *F, c.F); tri_refresh_values(c, *Mp, c.Mp); }
-      else { ilu0_factor(c, *F, c.F); ilu0_factor(c, *Mp, c.Mp); }
+      if (flavour == NSX_STATIONARY) { sgs_values(*F, c.F); sgs_values(*Mp, c.Mp); }
+      else { ilu(*F, c.F); ilu(*Mp, c.Mp); }
     } else if (type == 1) {
       Mp = &tri_plan(c, NSX_BLOCK_MP);
-      if (flavour == NSX_STATIONARY) amg_setup(c, c.F);
-      else { F = &tri_plan(c, NSX_BLOCK_F, ilu_variant); ilu0_factor(c, *F, c.F); }
-      ilu0_factor(c, *Mp, c.Mp);
+      if (flavour == NSX_STATIONARY) {
+        if (!(c.amg && reuse(c.amg_built_at))) { amg_setup(c, c.F); c.amg_built_at = c.solve_seq; c.stat_precond_builds++; }
+      } else { F = &tri_plan(c, NSX_BLOCK_F, ilu_variant); ilu(*F, c.F); }
+      ilu(*Mp, c.Mp);
     } else {
-      schur_complement(c);
+      // S and diag(F)^-1 belong together (vmult uses both): one decision for the pair and for the factors of S
+      const bool keep_S = c.S_symbolic && reuse(c.schur_built_at);
+      if (!keep_S) { schur_complement(c); c.schur_built_at = c.solve_seq; c.stat_precond_builds++; }
       // The unsteady aSIMPLE applies ONE ILU(0) sweep pair per block and iteration (NSSolver.hpp:294-350), so its outer iteration
       // count follows the quality of the factorisation: unless the caller chose an order, the blocks keep Ifpack's natural order
       // inside (ordering 3; measured on the reference's mesh: 81 k outer iterations against 107 k with the multicolour order)
       const int ord = (flavour == NSX_UNSTEADY && c.ordering_auto && c.ordering == 2) ? 3 : -1;
       F = &tri_plan(c, NSX_BLOCK_F, ilu_variant, ord); S = &tri_plan(c, NSX_BLOCK_S, 0, ord);
-      ilu0_factor(c, *F, c.F);
-      ilu0_factor(c, *S, c.S);
+      ilu(*F, c.F);
+      if (!(keep_S && S->factored && S->built_at >= 0)) { ilu0_factor(c, *S, c.S); S->built_at = c.solve_seq; c.stat_precond_builds++; }
       c.delta_p.alloc(c.nvec);
       c.delta_p.zero(c.stream);
     }
@@ -613,6 +627,7 @@ int solve_system(Ctx &c, int flavour, int solver, int prec, double tol, int max_
   if (prec < 0 || prec > 2)
     throw std::invalid_argument("Invalid preconditioner type. Use 0: blockDiagonal, 1: blockTriangular, 2: aSIMPLE.");
   c.stat_inner_F = c.stat_inner_S = c.stat_applies = 0;
+  c.solve_seq++;
   Control ctl(max_it, tol);
   Preconditioner pc(c, flavour, prec, alpha);
   pc.initialize();

@@ -164,6 +164,31 @@ def test_decoupled_view_changes_nothing_but_the_bytes():
     assert not dev.decoupled()
 
 
+def test_preconditioner_lag():
+    """NSX_OPT_PRECOND_LAG: two Newton systems in a row.  With lag 1 the second solve keeps the numeric preconditioner data of the
+    first (no build counted), still converges, and returns the increment of the rebuilt-every-solve run to the solver tolerance."""
+    out = []
+    for prec, flavour, mode in ((0, N.STATIONARY, N.MODE_NEWTON), (2, N.STATIONARY, N.MODE_NEWTON), (1, N.STATIONARY, N.MODE_NEWTON),
+                                (2, N.UNSTEADY, N.MODE_UNSTEADY_NEWTON)):
+        res = []
+        for lag in (0, 1):
+            d, orc, dev = make("quad", mode, 1 / 10.0, ordering=2, block_rows=256)
+            dev.set_option(N.OPT_PRECOND_LAG, lag)
+            rc, it1, _ = dev.solve(flavour, 1, prec, 1e-11, 20000)
+            assert rc == 0
+            b1 = dev.stat("PRECOND_BUILDS")
+            dev.update(0.3)                         # another linearisation point: every matrix value of F changes
+            dev.assemble(mode, False, 1 / 10.0, 0.01)
+            rc, it2, _ = dev.solve(flavour, 1, prec, 1e-11, 20000)
+            assert rc == 0
+            b2 = dev.stat("PRECOND_BUILDS")
+            res.append((it1, it2, b1, b2, dev.download(N.VEC_DELTA)))
+        print("prec", prec, "flavour", flavour, "rebuilt:", res[0][:4], "lag 1:", res[1][:4])
+        assert res[0][3] == 2 * res[0][2] and res[1][3] == res[1][2] and res[1][2] == res[0][2]
+        assert res[0][0] == res[1][0]
+        assert np.linalg.norm(res[0][4] - res[1][4]) <= 1e-8 * np.linalg.norm(res[0][4])
+
+
 def test_two_rank_local_preconditioners():
     """Owned ranges of a 2-rank partition: ILU / SGS drop the couplings across the range boundary
     (Ifpack overlap 0) on both sides alike."""
