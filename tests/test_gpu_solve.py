@@ -189,6 +189,30 @@ def test_preconditioner_lag():
         assert np.linalg.norm(res[0][4] - res[1][4]) <= 1e-8 * np.linalg.norm(res[0][4])
 
 
+@pytest.mark.parametrize("tri", [False, True])
+def test_poiseuille_known_answer_on_the_device(tri):
+    """The analytic check of tests/test_oracle.py::test_poiseuille_known_answer through the C ABI, library defaults: the Newton
+    residual of the interpolated Poiseuille state vanishes, and the Stokes solve from zero returns that state."""
+    from test_oracle import poiseuille
+    d = N.Disc.generate(8, 4, triangles=tri)
+    U, nu, p_out = 0.3, 0.02, 0.7
+    dev = N.Device(d, inlet_amplitude=U)
+    exact = poiseuille(d, U, nu, p_out)
+    zero = np.zeros(d.n)
+    dev.upload(N.VEC_SOLUTION, zero); dev.upload(N.VEC_SOLUTION_OLD, zero); dev.upload(N.VEC_DELTA, zero)
+    r0 = dev.assemble(N.MODE_NEWTON, True, nu, 0.01, p_out)
+    dev.upload(N.VEC_SOLUTION, exact)
+    r = dev.assemble(N.MODE_NEWTON, False, nu, 0.01, p_out)
+    assert r0 > 0.05 and r <= 1e-13 * r0
+    assert dev.assemble_residual(N.MODE_NEWTON, nu, 0.01, p_out) <= 1e-13 * r0   # the residual-only kernel too
+    dev.upload(N.VEC_SOLUTION, zero); dev.upload(N.VEC_DELTA, zero)
+    dev.assemble(N.MODE_STOKES, True, nu, 0.01, p_out)
+    rc, it, fr = dev.solve(N.STATIONARY, 1, 0, 1e-13, 5000)
+    assert rc == 0
+    dev.update(1.0)
+    assert np.abs(dev.download(N.VEC_SOLUTION) - exact).max() <= 1e-10 * np.abs(exact).max()
+
+
 def test_two_rank_local_preconditioners():
     """Owned ranges of a 2-rank partition: ILU / SGS drop the couplings across the range boundary
     (Ifpack overlap 0) on both sides alike."""

@@ -271,6 +271,40 @@ def test_schur_complement_product(prob):
     assert S.nnz >= ref.nnz     # the structural pattern (zeros kept), as EpetraExt's product
 
 
+def poiseuille(d, U, nu, p_out):
+    """Interpolant of the plane Poiseuille flow of the channel [0, 2.2] x [0, 0.41]: u_x = 4 U y (H - y) / H^2, u_y = 0,
+    p = p_out + 8 nu U / H^2 (L - x).  Parabola and linear pressure lie in Q3/Q2 and P2/P1, (u . grad) u = 0, the walls are
+    no-slip, the inlet profile is the reference's InletVelocity (NSSolverStationary.hpp:81-89) and the outlet traction is
+    -p_out n: it is the exact solution of the DISCRETE Stokes and Navier-Stokes problems on a mesh without the cylinder hole."""
+    X, comp = support_points(d)
+    H, L = 0.41, 2.2
+    ex = np.where(comp == 0, U * 4 * X[:, 1] * (H - X[:, 1]) / H ** 2, 0.0)
+    return np.where(comp == 2, p_out + 8 * nu * U / H ** 2 * (L - X[:, 0]), ex)
+
+
+@pytest.mark.parametrize("tri", [False, True])
+def test_poiseuille_known_answer(tri):
+    """A known answer that owes nothing to the restatement itself (8 x 4 cells: no cell centre falls inside the cylinder, so the
+    generated channel has no hole).  (a) The Newton-branch residual of the interpolated Poiseuille state vanishes to rounding --
+    viscous, convective, pressure, divergence and outlet terms, their signs and the quadrature at once; (b) the Stokes solve from
+    the zero state with the inlet values returns that state."""
+    d = N.Disc.generate(8, 4, triangles=tri)
+    assert d.ncells == (64 if tri else 32)
+    U, nu, p_out = 0.3, 0.02, 0.7
+    o = N.Oracle(d, inlet_amplitude=U)
+    exact = poiseuille(d, U, nu, p_out)
+    o.vec(0)[:] = 0; o.vec(2)[:] = 0
+    r0 = o.assemble(N.MODE_NEWTON, True, nu, p_out=p_out)
+    o.vec(0)[:] = exact
+    r = o.assemble(N.MODE_NEWTON, False, nu, p_out=p_out)
+    assert r0 > 0.05 and r <= 1e-13 * r0
+    o.vec(0)[:] = 0; o.vec(2)[:] = 0
+    o.assemble(N.MODE_STOKES, True, nu, p_out=p_out)
+    rc, it, fr, _ = o.solve(N.STATIONARY, 1, 0, 1e-13, 5000)
+    assert rc == 0
+    assert np.abs(o.vec(0) + o.vec(2) - exact).max() <= 1e-10 * np.abs(exact).max()
+
+
 @pytest.mark.parametrize("tri", [False, True])
 def test_lift_drag_of_hydrostatic_pressure(tri):
     """u = 0, p = const: the force on the closed cylinder boundary vanishes (divergence theorem) -- on the
