@@ -3,7 +3,8 @@
   compute-sanitizer --tool memcheck  python tools/sanitize_small.py --cap 10
   compute-sanitizer --tool racecheck python tools/sanitize_small.py --short
 Covers: assembly (4 modes) + residual-only, Dirichlet step, block SpMV, node / same-component / full views of F, block-local SGS and
-ILU(0) sweeps (orderings 2 and 3), natural and multicolour orders, device-driven inner FGMRES, CG, Schur product, AMG, lift / drag."""
+ILU(0) sweeps (orderings 2 and 3), natural and multicolour orders, device-driven inner FGMRES, CG, Schur product, AMG, lift / drag.
+(On the pool this round was built on compute-sanitizer is closed; without it the script is a 10-second run through all families.)"""
 import os
 import sys
 
@@ -14,7 +15,7 @@ sys.path.insert(0, ROOT)
 from navier_stokes_solver_b200 import binding as B  # noqa: E402
 
 short = "--short" in sys.argv
-cap = 3 if short else 400
+cap = 3 if short else 4000
 if "--cap" in sys.argv:
     cap = int(sys.argv[sys.argv.index("--cap") + 1])
 
@@ -30,7 +31,7 @@ def run(tri, ordering, cases):
         rc, it, fr = dev.solve(flavour, solver, prec, 1e-9 * r, cap)
         print(f"tri={int(tri)} ordering={ordering} flavour={flavour} solver={solver} prec={prec} mode={mode}: view {dev.view()} "
               f"|r|={r:.3e} res-only {rr:.3e} rc={rc} its={it} final {fr:.2e}", flush=True)
-        if cap >= 400 and rc != 0:
+        if cap >= 4000 and rc != 0:
             raise SystemExit("solve did not converge")
     dev.lift_drag(0.1)
 
