@@ -60,6 +60,8 @@ enum nsx_option {
                              complement) built in one solve also serve the next n solves -- Newton iterations / line-search states
                              change the matrices little, and FGMRES tolerates a lagged preconditioner; 0 (default): every solve
                              rebuilds them, as the initialize() calls of the reference do (NSSolverStationary.cpp:583,601,621) */
+  NSX_OPT_SWEEP_Q = 10,   /* block-local sweeps: entries of a row handled by one lane (4 default, 8, 16): fewer lanes and shuffle rounds per
+                             row against more padding in the matrix stream */
   NSX_OPT_HOST_INNER = 6  /* 1: the inner FGMRES solves run their recurrences on the host (one stream synchronisation per
                              iteration, round-1 behaviour); 0 (default): device-side Givens / convergence decision, the host
                              polls a mapped record and launches the next sweep speculatively */

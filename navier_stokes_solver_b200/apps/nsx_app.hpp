@@ -158,7 +158,7 @@ struct Problem {
     // library options from the environment; unset = the library's defaults
     const struct { const char *env; int opt; } opts[] = {{"NSX_ORDERING", NSX_OPT_ORDERING}, {"NSX_ORTHO", NSX_OPT_ORTHO}, {"NSX_BLOCK_ROWS", NSX_OPT_BLOCK_ROWS},
                                                         {"NSX_DECOUPLE", NSX_OPT_DECOUPLE}, {"NSX_HOST_INNER", NSX_OPT_HOST_INNER}, {"NSX_VERBOSE", NSX_OPT_VERBOSE},
-                                                        {"NSX_L2_HINTS", NSX_OPT_L2_HINTS}, {"NSX_PRECOND_LAG", NSX_OPT_PRECOND_LAG}};
+                                                        {"NSX_L2_HINTS", NSX_OPT_L2_HINTS}, {"NSX_PRECOND_LAG", NSX_OPT_PRECOND_LAG}, {"NSX_SWEEP_Q", NSX_OPT_SWEEP_Q}};
     for (const auto &o : opts)
       if (const char *v = std::getenv(o.env)) check(ctx, nsx_set_option(ctx, o.opt, std::atoll(v)), o.env);
     const bool local = ranks.size > 1;

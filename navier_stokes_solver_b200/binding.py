@@ -30,7 +30,7 @@ MODE_STOKES, MODE_NEWTON, MODE_UNSTEADY_FIRST, MODE_UNSTEADY_NEWTON = 0, 1, 2, 3
 VEC_SOLUTION, VEC_SOLUTION_OLD, VEC_DELTA, VEC_RESIDUAL, VEC_EVAL, VEC_TMP0, VEC_TMP1 = 0, 1, 2, 3, 4, 5, 6
 STATIONARY, UNSTEADY = 0, 1
 NSX_OK, NSX_E_NOCONV, NSX_E_BADARG, NSX_E_CUDA, NSX_E_COMM, NSX_E_STATE = 0, 1, 2, 3, 4, 5
-OPT_ORDERING, OPT_VERBOSE, OPT_ORTHO, OPT_COOP_SWEEP, OPT_STREAM_SPMV, OPT_BLOCK_ROWS, OPT_HOST_INNER, OPT_DECOUPLE, OPT_L2_HINTS, OPT_PRECOND_LAG = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
+OPT_ORDERING, OPT_VERBOSE, OPT_ORTHO, OPT_COOP_SWEEP, OPT_STREAM_SPMV, OPT_BLOCK_ROWS, OPT_HOST_INNER, OPT_DECOUPLE, OPT_L2_HINTS, OPT_PRECOND_LAG, OPT_SWEEP_Q = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 STAT = dict(INNER_F=0, INNER_S=1, PRECOND_APPLIES=2, KERNEL_LAUNCHES=3, LEVELS_F=4, LEVELS_MP=5, LEVELS_S=6,
             SPMV_CALLS=7, ASSEMBLY_COLOURS=8, ASSEMBLY_TABLES=9, LAST_STEP=10, HALO_EXCHANGES=11, ALLREDUCES=12, F_DECOUPLED=13, SWEEP_BYTES_F=14, SPMV_BYTES_F=15, PRECOND_BUILDS=16)
 # every entry point include/nsx.h declares (tests check that the library exports each one)

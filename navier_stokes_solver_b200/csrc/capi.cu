@@ -145,6 +145,9 @@ int nsx_set_option(nsx_ctx *ctx, int option, int64_t value) {
         ctx->stream_spmv = (int)value; break;
       case NSX_OPT_HOST_INNER: ctx->host_inner = value != 0; break;
       case NSX_OPT_L2_HINTS: ctx->l2_hints = value != 0; break;
+      case NSX_OPT_SWEEP_Q:
+        if (value != 4 && value != 8 && value != 16) throw std::invalid_argument("entries per lane must be 4, 8 or 16");
+        ctx->sweep_q = (int)value; ctx->tri.clear(); ctx->schur_built_at = ctx->amg_built_at = -1; break;
       case NSX_OPT_PRECOND_LAG:
         if (value < 0 || value > 1000000) throw std::invalid_argument("preconditioner lag must be a solve count >= 0");
         ctx->precond_lag = (int)value; break;

@@ -163,6 +163,7 @@ struct Ctx {
   // NSX_OPT_PRECOND_LAG: numeric preconditioner data (ILU factors, sweep values, AMG hierarchy, Schur complement) built in solve s
   // serve the solves s+1 .. s+lag as well (0, default: rebuilt in every solve, as the reference's initialize() calls do)
   int precond_lag = 0;
+  int sweep_q = 4;        // NSX_OPT_SWEEP_Q: entries per lane of the block-local sweeps' passes (4, 8 or 16)
   long long solve_seq = 0, schur_built_at = -1, amg_built_at = -1, stat_precond_builds = 0;
   bool ordering_auto = true;   // NSX_OPT_ORDERING never set: preconditioners that are a single ILU(0) application per iteration use ordering 3
   int block_rows = 0;    // ordering 2: target rows per block (0: n / #SMs clamped to [512, 4096])

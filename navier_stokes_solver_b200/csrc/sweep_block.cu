@@ -329,9 +329,14 @@ void bl_build(Ctx &c, TriPlan &P) {
         std::iota(rows.begin(), rows.end(), lo);
         std::stable_sort(rows.begin(), rows.end(), [&](int64_t u, int64_t v) { return count(u) > count(v); });
         const int maxc = rows.empty() ? 0 : count(rows[0]);
+        // entries per lane: 4, or up to NSX_OPT_SWEEP_Q when the level's longest row has that many (fewer lanes per row, fewer
+        // shuffle rounds, more padding in the stream)
         int Q = 4;
+        while (Q < c.sweep_q && Q < maxc) Q *= 2;
         while (Q * 32 < maxc) Q *= 2;   // a row's lanes stay inside one warp
         if (maxc == 0) Q = 1;
+        // warps of a pass: what the ring takes (values + columns + lane / row tables of a pass <= PASS_BYTES_MAX)
+        const int max_warps = std::max(1, std::min(NC / 32, (PASS_BYTES_MAX - 64) / (32 * (Q * 10 + 2 + 10))));
         size_t at = 0;
         while (at < rows.size()) {
           // first-fit packing of the rows' lane groups into the warps of one pass
@@ -343,7 +348,7 @@ void bl_build(Ctx &c, TriPlan &P) {
             int w = 0;
             while (w < (int)room.size() && room[w] < k) ++w;
             if (w == (int)room.size()) {
-              if ((int)room.size() == NC / 32) break;
+              if ((int)room.size() == max_warps) break;
               room.push_back(32);
             }
             segs.push_back(Seg{rows[next], w * 32 + (32 - room[w]), k});

@@ -26,6 +26,7 @@ ap.add_argument("--max-outer", type=int, default=20000)
 ap.add_argument("--prec", type=int, default=0)
 ap.add_argument("--verbose", type=int, default=1)
 ap.add_argument("--l2-hints", type=int, default=1)
+ap.add_argument("--sweep-q", type=int, default=4)
 a = ap.parse_args()
 nx, ny = (int(v) for v in a.mesh.split(","))
 t0 = time.perf_counter()
@@ -35,6 +36,7 @@ dev = B.Device(d, ordering=a.ordering, ortho=a.ortho, block_rows=a.block_rows or
 dev.set_option(B.OPT_VERBOSE, a.verbose)
 dev.set_option(B.OPT_HOST_INNER, a.host_inner)
 dev.set_option(B.OPT_L2_HINTS, a.l2_hints)
+dev.set_option(B.OPT_SWEEP_Q, a.sweep_q)
 out = {"mesh": a.mesh, "cells": d.ncells, "dofs": d.n, "ordering": a.ordering, "host_inner": a.host_inner, "ortho": a.ortho,
        "disc_s": t1 - t0, "device_setup_s": time.perf_counter() - t1}
 nu = 0.1
