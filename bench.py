@@ -144,16 +144,37 @@ class CpuSampler:
         return self._capped(self.cap)
 
 
-def outer_total_fixture(mesh, solver, prec):
-    """Outer iteration count of the FULL first-step solve by the CPU oracle itself (profiles/oracle_full_solves.json, written by
-    tools/oracle_full_solve.py in the build container: the solve takes about an hour of 8 cores, far beyond a bench lease)."""
+def outer_total_fixture(mesh, solver, prec, blocks=None):
+    """Iteration counts of the FULL first-step solve by the CPU oracle itself (profiles/oracle_full_solves.json, written by
+    tools/oracle_full_solve.py in the build container: the solve takes hours of 8 cores, far beyond a bench lease).  Prefers the
+    record taken with `blocks` rank-local blocks (the preconditioner depends on the partition)."""
     p = os.path.join(ROOT, "profiles", "oracle_full_solves.json")
+    best = None
     if os.path.exists(p):
         with open(p) as f:
             for rec in json.load(f):
                 if rec["mesh"] == mesh and rec["solver"] == solver and rec["prec"] == prec:
-                    return rec
-    return None
+                    if best is None or (blocks is not None and rec.get("blocks") == blocks):
+                        best = rec
+    return best
+
+
+def extrapolation(smp, fixture, cpu_outer_total, fallback_outer, fallback_text):
+    """(scale of the capped solve's time, text).  The cost of the solve is its inner iterations, so the sample is scaled by the
+    ratio of inner F iterations when the oracle's full solve is on record; by outer iterations otherwise."""
+    if smp["converged"]:
+        return 1.0, smp["outer_done"], None
+    if cpu_outer_total:
+        return max(1.0, cpu_outer_total / smp["outer_done"]), cpu_outer_total, f"linearly in outer iterations to {cpu_outer_total} (--cpu-outer-total)"
+    if fixture:
+        src = f"{fixture.get('source', 'the oracle`s own full solve')}, {fixture.get('blocks', '?')} blocks, profiles/oracle_full_solves.json"
+        if fixture.get("inner_F") and smp.get("inner_F"):
+            return (max(1.0, fixture["inner_F"] / smp["inner_F"]), fixture["outer"],
+                    f"by inner F iterations, {smp['inner_F']} done of {fixture['inner_F']} ({fixture['outer']} outer iterations) in {src}")
+        return max(1.0, fixture["outer"] / smp["outer_done"]), fixture["outer"], f"linearly in outer iterations to {fixture['outer']}, the count of {src}"
+    if fallback_outer:
+        return max(1.0, fallback_outer / smp["outer_done"]), fallback_outer, f"linearly in outer iterations to {fallback_outer}, the count of {fallback_text}"
+    return 1.0, smp["outer_done"], "no full count known: NOT extrapolated"
 
 
 def workload_name(args, nx, ny):
@@ -166,11 +187,11 @@ def run_reference(args, emit):
     image, so the timed code is the oracle port of the reference path (oracle/, OpenMP over all host cores, one rank-local
     preconditioner block per thread as under mpirun).  A whole step of the 300x100 configuration takes the CPU the better
     part of an hour, so each bench step is a BOUNDED SAMPLE: both assemblies in full plus the solve capped at a number of outer
-    iterations that lasts about --cpu-sample-s seconds; `value` is that sample extrapolated linearly in outer iterations to
-    the count of the full solve (early outer iterations are the cheap ones -- their inner solves converge fastest -- so the
-    scaling favours the CPU).  The line says `extrapolated`, and carries the measured seconds beside the extrapolated ones.
-    The full count comes from the oracle's own complete solve (profiles/oracle_full_solves.json) or --cpu-outer-total; meshes
-    small enough are simply solved in full (no extrapolation)."""
+    iterations that lasts about --cpu-sample-s seconds; `value` is that sample extrapolated to the full solve by the ratio of
+    inner F iterations (where the time goes), the full counts being those of the oracle's own complete solve of this step
+    (profiles/oracle_full_solves.json: 685 outer / 172 072 inner iterations with 16 rank-local blocks, 5.1 h in the build
+    container), or linearly in outer iterations to --cpu-outer-total.  The line says `extrapolated`, and carries the measured
+    seconds beside the extrapolated ones; meshes small enough are simply solved in full (no extrapolation)."""
     from navier_stokes_solver_b200 import binding as B
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -178,16 +199,15 @@ def run_reference(args, emit):
     nx, ny = parse_mesh(args.mesh)
     d = B.Disc.generate(nx, ny)
     nu = 1.0 / 10.0
-    fixture = outer_total_fixture(args.mesh, args.solver, args.prec)
-    total = args.cpu_outer_total or (fixture["outer"] if fixture else 0)
     small = d.n < 40000   # solved in full
     times, meas = [], []
     smp = None
     sampler = CpuSampler(nx, ny, args.solver, args.prec, args.tol, nu)
+    fixture = outer_total_fixture(args.mesh, args.solver, args.prec, sampler.threads)
+    scale, total, how = 1.0, 0, None
     for s in range(args.warmup + args.steps):
         smp = sampler.sample(20000 if small else args.cpu_outer_cap, target_s=0.0 if small else 0.5 * args.cpu_sample_s)
-        full = smp["converged"]
-        scale = 1.0 if full else max(1.0, (total or smp["outer_done"]) / smp["outer_done"])
+        scale, total, how = extrapolation(smp, fixture, args.cpu_outer_total, 0, "")
         if s >= args.warmup:
             times.append(2 * smp["t_asm"] + smp["t_solve"] * scale)
             meas.append(2 * smp["t_asm"] + smp["t_solve"])
@@ -197,15 +217,14 @@ def run_reference(args, emit):
     sample = (f"oracle port, mesh cut into {cores} rank-local blocks on {cores} host threads (as mpirun -n {cores}): 2 full assemblies "
               f"({smp['t_asm']:.2f} s each) + solve " +
               (f"run to convergence ({smp['outer_done']} outer iterations, {smp['t_solve']:.2f} s)" if not extrapolated else
-               f"capped at {smp['outer_done']} outer iterations ({smp['t_solve']:.2f} s measured), extrapolated linearly to {total or smp['outer_done']} outer iterations "
-               f"({(fixture.get('source') or 'the count of the oracle`s own full solve') + ', profiles/oracle_full_solves.json' if fixture and not args.cpu_outer_total else '--cpu-outer-total' if args.cpu_outer_total else 'no full count known: NOT extrapolated'})"))
+               f"capped at {smp['outer_done']} outer iterations ({smp['t_solve']:.2f} s measured), extrapolated {how}"))
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": val * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference", "extrapolated": extrapolated,
             "measured_sample_s": float(np.mean(meas)),
             "config": {"workload": workload_name(args, nx, ny), "cells": d.ncells, "dofs": d.n},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "extrapolated": extrapolated,
-                             "measured_s": float(np.mean(meas)), "outer_done": smp["outer_done"], "outer_total": total or smp["outer_done"]},
+                             "measured_s": float(np.mean(meas)), "outer_done": smp["outer_done"], "outer_total": total or smp["outer_done"], "scale": scale},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -596,17 +615,15 @@ def main():
     }
     if rank == 0 and not args.no_cpu and world == 1:
         smp = CpuSampler(nx, ny, args.solver, args.prec, args.tol, nu).sample(args.cpu_outer_cap, target_s=args.cpu_sample_s)
-        fixture = outer_total_fixture(args.mesh, args.solver, args.prec)
-        total = args.cpu_outer_total or (fixture["outer"] if fixture else stats["outer"])
-        src = "--cpu-outer-total" if args.cpu_outer_total else ((fixture.get("source") or "the oracle's own full solve") + " (profiles/oracle_full_solves.json)" if fixture else "this run's GPU solve")
+        fixture = outer_total_fixture(args.mesh, args.solver, args.prec, smp["threads"])
+        scale, total, how = extrapolation(smp, fixture, args.cpu_outer_total, stats["outer"], "this run's GPU solve")
         extrapolated = not smp["converged"]
-        scale = max(1.0, total / smp["outer_done"]) if extrapolated else 1.0
         cpu_val = 2 * smp["t_asm"] + smp["t_solve"] * scale
         cores = smp["threads"]
         line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "extrapolated": extrapolated,
-                                "measured_s": 2 * smp["t_asm"] + smp["t_solve"], "outer_done": smp["outer_done"], "outer_total": total if extrapolated else smp["outer_done"],
+                                "measured_s": 2 * smp["t_asm"] + smp["t_solve"], "outer_done": smp["outer_done"], "outer_total": total, "scale": scale,
                                 "sample": f"oracle port, mesh cut into {cores} rank-local blocks on {cores} host threads (as mpirun -n {cores}): 2 full assemblies ({smp['t_asm']:.2f} s each) + solve " +
-                                          (f"capped at {smp['outer_done']} outer iterations ({smp['t_solve']:.2f} s measured), extrapolated linearly to {total} outer iterations, the count of {src}"
+                                          (f"capped at {smp['outer_done']} outer iterations ({smp['t_solve']:.2f} s measured), extrapolated {how}"
                                            if extrapolated else f"run to convergence ({smp['outer_done']} outer iterations, {smp['t_solve']:.2f} s)")}
     if rank == 0:
         emit(line)
