@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Runs the CPU oracle's FULL first-step solve of a bench configuration (README: -m 300,100 -s 1 -p 0 -t 1e-10, Stokes branch,
 nu = 1/10) and records its iteration counts in profiles/oracle_full_solves.json.  bench.py extrapolates its bounded CPU samples
-to these counts.  Takes about an hour of 8 cores at 300x100; run in the build container, not in a bench lease.
+to these counts.  Takes hours at 300x100 (5.1 h on 7 threads of the 8-core build container); not something for a bench lease.
 usage: oracle_full_solve.py NX,NY BLOCKS [THREADS]"""
 import json
 import os
