@@ -133,6 +133,26 @@ def test_block_local_sweeps_match_oracle(setup, rows, block, kind):
         dev.set_option(N.OPT_ORDERING, 0)
 
 
+@pytest.mark.parametrize("q", [8, 16])
+@pytest.mark.parametrize("block,kind", [(N.BLOCK_F, 0), (N.BLOCK_F, 1), (N.BLOCK_MP, 1)])
+def test_block_local_sweeps_entries_per_lane(setup, block, kind, q):
+    """NSX_OPT_SWEEP_Q: 8 or 16 entries of a row per lane (fewer lanes and shuffle rounds per row) is only another summation
+    order inside a row -- same answer against the oracle with the same blocks and sequences."""
+    d, orc, dev = setup
+    dev.set_option(N.OPT_SWEEP_Q, q)
+    use_block_local(dev, 300)
+    try:
+        blocks = mirror_blocks(dev, orc)
+        n = d.n_u if block == N.BLOCK_F else d.n_p
+        x = np.random.default_rng(13).uniform(-1, 1, n)
+        assert rel(dev.inner_apply(block, kind, x), orc.inner_apply(block, kind, x)) < 1e-11
+    finally:
+        orc.set_blocks(0); orc.set_blocks(1)
+        dev.set_option(N.OPT_SWEEP_Q, 4)
+        dev.set_option(N.OPT_BLOCK_ROWS, 0)
+        dev.set_option(N.OPT_ORDERING, 0)
+
+
 @pytest.mark.parametrize("ordering", [0, 1, 2])
 @pytest.mark.parametrize("block,kind", [(N.BLOCK_F, 0), (N.BLOCK_F, 1), (N.BLOCK_MP, 0), (N.BLOCK_MP, 1)])
 def test_inner_preconditioners_by_definition(setup, ordering, block, kind):
