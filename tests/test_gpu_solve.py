@@ -205,6 +205,9 @@ def test_poiseuille_known_answer_on_the_device(tri):
     r = dev.assemble(N.MODE_NEWTON, False, nu, 0.01, p_out)
     assert r0 > 0.05 and r <= 1e-13 * r0
     assert dev.assemble_residual(N.MODE_NEWTON, nu, 0.01, p_out) <= 1e-13 * r0   # the residual-only kernel too
+    dev.upload(N.VEC_SOLUTION_OLD, exact)                                         # a steady state of the time stepping as well
+    assert dev.assemble(N.MODE_UNSTEADY_NEWTON, False, nu, 0.01, p_out) <= 1e-13 * r0
+    dev.upload(N.VEC_SOLUTION_OLD, zero)
     dev.upload(N.VEC_SOLUTION, zero); dev.upload(N.VEC_DELTA, zero)
     dev.assemble(N.MODE_STOKES, True, nu, 0.01, p_out)
     rc, it, fr = dev.solve(N.STATIONARY, 1, 0, 1e-13, 5000)

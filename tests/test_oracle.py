@@ -298,6 +298,12 @@ def test_poiseuille_known_answer(tri):
     o.vec(0)[:] = exact
     r = o.assemble(N.MODE_NEWTON, False, nu, p_out=p_out)
     assert r0 > 0.05 and r <= 1e-13 * r0
+    # ... and it is a steady state of the time-stepping scheme: u_old = u makes the unsteady Newton residual vanish too, while a
+    # different old state leaves exactly the mass term (u - u_old) / dt behind
+    o.vec(1)[:] = exact
+    assert o.assemble(N.MODE_UNSTEADY_NEWTON, False, nu, 0.01, p_out) <= 1e-13 * r0
+    o.vec(1)[:] = 0.5 * exact
+    assert o.assemble(N.MODE_UNSTEADY_NEWTON, False, nu, 0.01, p_out) > 1e-3
     o.vec(0)[:] = 0; o.vec(2)[:] = 0
     o.assemble(N.MODE_STOKES, True, nu, p_out=p_out)
     rc, it, fr, _ = o.solve(N.STATIONARY, 1, 0, 1e-13, 5000)
