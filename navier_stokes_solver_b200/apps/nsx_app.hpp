@@ -19,6 +19,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <future>
+#include <memory>
 #include <iostream>
 #include <sstream>
 #include <stdexcept>
@@ -130,7 +132,10 @@ struct Problem {
   nsx_ctx *ctx = nullptr;
   int64_t n_u_owned = 0, n_p_owned = 0;
 
+  mutable std::future<void> vtu_writer;   // the output file being written behind the solver (write_vtu)
+
   ~Problem() {
+    if (vtu_writer.valid()) vtu_writer.wait();
     if (ctx) nsx_destroy(ctx);
     if (view && view != global) nsx_disc_free(view);
     if (global) nsx_disc_free(global);
@@ -206,48 +211,69 @@ struct Problem {
 
   // Minimal stand-in for DataOut::write_vtu_with_pvtu_record (NSSolverStationary.cpp:765-800; deal.II keeps the real
   // one): this rank's owned cells as linear cells with the vertex values of velocity and pressure.
-  void write_vtu(const std::string &stem, unsigned index) const {
-    const int64_t ncells = info(NSX_DI_NCELLS), nvpc = info(NSX_DI_NVPC), dpc = info(NSX_DI_DOFS_PER_CELL);
-    const int64_t n_u = info(NSX_DI_N_U);
-    std::vector<double> sol((size_t)(n_u_owned + n_p_owned));
-    check(ctx, nsx_vec_download(ctx, NSX_VEC_SOLUTION, sol.data()), "nsx_vec_download");
-    std::vector<double> gu, gp;
-    if (ranks.size > 1) {
-      gu.resize((size_t)(n_u - n_u_owned)); gp.resize((size_t)(info(NSX_DI_N_P) - n_p_owned));
-      check(ctx, nsx_halo_exchange(ctx, NSX_VEC_SOLUTION), "nsx_halo_exchange");
-      check(ctx, nsx_vec_download_ghosts(ctx, NSX_VEC_SOLUTION, gu.data(), gp.data()), "nsx_vec_download_ghosts");
+  // Asynchronous: the calling thread only takes a snapshot of the solution (device -> host, plus the ghost values on a
+  // partitioned run); formatting and writing happen on a worker thread while the solver goes on -- one file in flight, the
+  // next call (or the destructor) waits for it and rethrows what it threw.  NSX_SYNC_OUTPUT=1 writes on the calling thread.
+  struct VtuJob {
+    std::vector<double> sol, gu, gp;
+    std::vector<int64_t> cells;
+    const double *cv; const uint32_t *cd;
+    int64_t nvpc, dpc, n_u, n_u_owned, n_p_owned;
+    int rank;
+    std::string name;
+    void run() const {
+      auto u_at = [&](uint32_t d) { return d < (uint64_t)n_u_owned ? sol[d] : gu[d - n_u_owned]; };
+      auto p_at = [&](uint32_t d) { const int64_t q = (int64_t)d - n_u; return q < n_p_owned ? sol[n_u_owned + q] : gp[q - n_p_owned]; };
+      std::ofstream f(name);
+      if (!f) throw std::runtime_error("cannot open " + name);
+      const int64_t nc = (int64_t)cells.size(), np = nc * nvpc;
+      f << "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n"
+        << "<Piece NumberOfPoints=\"" << np << "\" NumberOfCells=\"" << nc << "\">\n<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n";
+      f.precision(12);
+      for (int64_t c : cells) for (int v = 0; v < nvpc; ++v) f << cv[(c * nvpc + v) * 2] << " " << cv[(c * nvpc + v) * 2 + 1] << " 0\n";
+      f << "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int64\" Name=\"connectivity\" format=\"ascii\">\n";
+      // deal.II numbers quad vertices lexicographically; VTK_QUAD wants them counter-clockwise
+      const int quad_order[4] = {0, 1, 3, 2}, tri_order[3] = {0, 1, 2};
+      for (int64_t k = 0; k < nc; ++k) { for (int v = 0; v < nvpc; ++v) f << k * nvpc + (nvpc == 4 ? quad_order[v] : tri_order[v]) << " "; f << "\n"; }
+      f << "</DataArray>\n<DataArray type=\"Int64\" Name=\"offsets\" format=\"ascii\">\n";
+      for (int64_t k = 1; k <= nc; ++k) f << k * nvpc << "\n";
+      f << "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n";
+      for (int64_t k = 0; k < nc; ++k) f << (nvpc == 4 ? 9 : 5) << "\n";
+      f << "</DataArray>\n</Cells>\n<PointData Vectors=\"velocity\" Scalars=\"pressure\">\n<DataArray type=\"Float64\" Name=\"velocity\" NumberOfComponents=\"3\" format=\"ascii\">\n";
+      // FESystem cell-local order: vertex v carries [u_x, u_y, p] at 3v, 3v+1, 3v+2
+      for (int64_t c : cells) for (int v = 0; v < nvpc; ++v) f << u_at(cd[c * dpc + 3 * v]) << " " << u_at(cd[c * dpc + 3 * v + 1]) << " 0\n";
+      f << "</DataArray>\n<DataArray type=\"Float64\" Name=\"pressure\" format=\"ascii\">\n";
+      for (int64_t c : cells) for (int v = 0; v < nvpc; ++v) f << p_at(cd[c * dpc + 3 * v + 2]) << "\n";
+      f << "</DataArray>\n</PointData>\n<CellData Scalars=\"partitioning\">\n<DataArray type=\"Float64\" Name=\"partitioning\" format=\"ascii\">\n";
+      for (int64_t k = 0; k < nc; ++k) f << rank << "\n";
+      f << "</DataArray>\n</CellData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n";
+      if (!f) throw std::runtime_error("error writing " + name);
     }
-    auto u_at = [&](uint32_t d) { return d < (uint64_t)n_u_owned ? sol[d] : gu[d - n_u_owned]; };
-    auto p_at = [&](uint32_t d) { const int64_t q = (int64_t)d - n_u; return q < n_p_owned ? sol[n_u_owned + q] : gp[q - n_p_owned]; };
-    const double *cv = arr<double>(NSX_DA_CELL_VERTICES);
-    const uint32_t *cd = arr<uint32_t>(NSX_DA_CELL_DOFS);
+  };
+
+  void write_vtu(const std::string &stem, unsigned index) const {
+    auto job = std::make_shared<VtuJob>();
+    const int64_t ncells = info(NSX_DI_NCELLS);
+    job->nvpc = info(NSX_DI_NVPC); job->dpc = info(NSX_DI_DOFS_PER_CELL); job->n_u = info(NSX_DI_N_U);
+    job->n_u_owned = n_u_owned; job->n_p_owned = n_p_owned; job->rank = ranks.rank;
+    job->sol.resize((size_t)(n_u_owned + n_p_owned));
+    check(ctx, nsx_vec_download(ctx, NSX_VEC_SOLUTION, job->sol.data()), "nsx_vec_download");
+    if (ranks.size > 1) {
+      job->gu.resize((size_t)(job->n_u - n_u_owned)); job->gp.resize((size_t)(info(NSX_DI_N_P) - n_p_owned));
+      check(ctx, nsx_halo_exchange(ctx, NSX_VEC_SOLUTION), "nsx_halo_exchange");
+      check(ctx, nsx_vec_download_ghosts(ctx, NSX_VEC_SOLUTION, job->gu.data(), job->gp.data()), "nsx_vec_download_ghosts");
+    }
+    job->cv = arr<double>(NSX_DA_CELL_VERTICES);   // the discretisation outlives the writer (~Problem waits for it)
+    job->cd = arr<uint32_t>(NSX_DA_CELL_DOFS);
     const uint8_t *owned = ranks.size > 1 ? arr<uint8_t>(NSX_DA_CELL_OWNED) : nullptr;
+    for (int64_t c = 0; c < ncells; ++c) if (!owned || owned[c]) job->cells.push_back(c);
     char name[256];
     snprintf(name, sizeof name, "%s_%u.%d.vtu", stem.c_str(), index, ranks.rank);
-    std::ofstream f(name);
-    std::vector<int64_t> cells;
-    for (int64_t c = 0; c < ncells; ++c) if (!owned || owned[c]) cells.push_back(c);
-    const int64_t nc = (int64_t)cells.size(), np = nc * nvpc;
-    f << "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n"
-      << "<Piece NumberOfPoints=\"" << np << "\" NumberOfCells=\"" << nc << "\">\n<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n";
-    f.precision(12);
-    for (int64_t c : cells) for (int v = 0; v < nvpc; ++v) f << cv[(c * nvpc + v) * 2] << " " << cv[(c * nvpc + v) * 2 + 1] << " 0\n";
-    f << "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int64\" Name=\"connectivity\" format=\"ascii\">\n";
-    // deal.II numbers quad vertices lexicographically; VTK_QUAD wants them counter-clockwise
-    const int quad_order[4] = {0, 1, 3, 2}, tri_order[3] = {0, 1, 2};
-    for (int64_t k = 0; k < nc; ++k) { for (int v = 0; v < nvpc; ++v) f << k * nvpc + (nvpc == 4 ? quad_order[v] : tri_order[v]) << " "; f << "\n"; }
-    f << "</DataArray>\n<DataArray type=\"Int64\" Name=\"offsets\" format=\"ascii\">\n";
-    for (int64_t k = 1; k <= nc; ++k) f << k * nvpc << "\n";
-    f << "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n";
-    for (int64_t k = 0; k < nc; ++k) f << (nvpc == 4 ? 9 : 5) << "\n";
-    f << "</DataArray>\n</Cells>\n<PointData Vectors=\"velocity\" Scalars=\"pressure\">\n<DataArray type=\"Float64\" Name=\"velocity\" NumberOfComponents=\"3\" format=\"ascii\">\n";
-    // FESystem cell-local order: vertex v carries [u_x, u_y, p] at 3v, 3v+1, 3v+2
-    for (int64_t c : cells) for (int v = 0; v < nvpc; ++v) f << u_at(cd[c * dpc + 3 * v]) << " " << u_at(cd[c * dpc + 3 * v + 1]) << " 0\n";
-    f << "</DataArray>\n<DataArray type=\"Float64\" Name=\"pressure\" format=\"ascii\">\n";
-    for (int64_t c : cells) for (int v = 0; v < nvpc; ++v) f << p_at(cd[c * dpc + 3 * v + 2]) << "\n";
-    f << "</DataArray>\n</PointData>\n<CellData Scalars=\"partitioning\">\n<DataArray type=\"Float64\" Name=\"partitioning\" format=\"ascii\">\n";
-    for (int64_t k = 0; k < nc; ++k) f << ranks.rank << "\n";
-    f << "</DataArray>\n</CellData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n";
+    job->name = name;
+    if (vtu_writer.valid()) vtu_writer.get();   // one file in flight
+    const char *sync = std::getenv("NSX_SYNC_OUTPUT");
+    if (sync && std::atoi(sync)) job->run();
+    else vtu_writer = std::async(std::launch::async, [job] { job->run(); });
   }
 };
 

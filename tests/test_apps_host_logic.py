@@ -26,7 +26,7 @@ def cpu_apps(tmp_path_factory):
                     os.path.join(N.ROOT, "tests", "shim", "nsx_over_oracle.cpp"), f"{CSRC}/hostsetup.cpp", f"{CSRC}/capi_host.cpp",
                     "-L", ORC, "-loracle", f"-Wl,-rpath,{ORC}"], check=True)
     for src, exe in (("stationary_main.cpp", "StationaryNSSolver_cpu"), ("unsteady_main.cpp", "NSSolver_cpu")):
-        subprocess.run([gxx, "-O2", "-std=c++17", "-Wno-reorder", f"{APPS}/{src}", "-o", f"{t}/{exe}", "-L", t, "-lnsx_shim", f"-Wl,-rpath,{t}"], check=True)
+        subprocess.run([gxx, "-O2", "-std=c++17", "-Wno-reorder", "-pthread", f"{APPS}/{src}", "-o", f"{t}/{exe}", "-L", t, "-lnsx_shim", f"-Wl,-rpath,{t}"], check=True)
     return t
 
 
@@ -95,3 +95,41 @@ def test_bad_preconditioner_ends_like_the_reference(cpu_apps, tmp_path):
     assert r.returncode != 0
     assert "Invalid preconditioner type. Use 0: blockDiagonal, 1: blockTriangular, 2: aSIMPLE." in r.stderr
     assert "Newton iteration 0/15" in r.stdout
+
+
+def test_output_files_written_behind_the_solver(cpu_apps, tmp_path):
+    """The VTU stand-in (NSSolverStationary.cpp:765-800, NSSolver.cpp:788-793) is written by a worker thread from a snapshot of
+    the solution: same bytes as the synchronous writer (NSX_SYNC_OUTPUT=1), well-formed, one piece per rank with the owned cells,
+    and the unsteady executable leaves one file per time step."""
+    import xml.etree.ElementTree as ET
+    outs = {}
+    for mode in ("async", "sync"):
+        d = tmp_path / mode
+        d.mkdir()
+        env = dict(os.environ)
+        env.pop("NSX_NO_OUTPUT", None)
+        if mode == "sync":
+            env["NSX_SYNC_OUTPUT"] = "1"
+        r = subprocess.run([f"{cpu_apps}/StationaryNSSolver_cpu", "-m", "8,4", "-r", "10", "-s", "1", "-p", "2", "-t", "1e-8"], capture_output=True,
+                           text=True, timeout=900, cwd=d, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert "Output written to output-stokes" in r.stdout
+        outs[mode] = (d / "output-stokes_0.0.vtu").read_bytes()
+    assert outs["async"] == outs["sync"] and len(outs["sync"]) > 1000
+    root = ET.fromstring(outs["async"])
+    piece = root.find("UnstructuredGrid/Piece")
+    disc = N.Disc.generate(8, 4)
+    assert int(piece.get("NumberOfCells")) == disc.ncells and int(piece.get("NumberOfPoints")) == 4 * disc.ncells
+    vel = np.array(piece.find("PointData/DataArray[@Name='velocity']").text.split(), dtype=float).reshape(-1, 3)
+    assert vel.shape[0] == 4 * disc.ncells and np.abs(vel[:, 0]).max() > 0.01 and (vel[:, 2] == 0).all()
+    d = tmp_path / "unsteady"
+    d.mkdir()
+    env = dict(os.environ, NSX_MAX_TIME_STEPS="2")
+    env.pop("NSX_NO_OUTPUT", None)
+    r = subprocess.run([f"{cpu_apps}/NSSolver_cpu", "-m", "8,4", "-r", "11", "-T", "0.03,0.01", "-s", "1", "-p", "2", "-t", "1e-6"], capture_output=True,
+                       text=True, timeout=900, cwd=d, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    files = sorted(p.name for p in d.glob("output_*.vtu"))
+    assert len(files) >= 2, files
+    for name in files:
+        ET.fromstring((d / name).read_bytes())
