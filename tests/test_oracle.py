@@ -4,6 +4,8 @@ scipy's direct solver and sparse products, and dense restatements of ILU(0) / SG
 
 The reference holds no golden vector for this path: parity is UNPINNED at the
 deal.II / Trilinos boundary and these identities are what anchors the oracle instead."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -381,3 +383,101 @@ def test_amg_oracle_contracts_and_scales():
     rc, it, fr, inner = o.solve(N.STATIONARY, 1, 1, 1e-10, 500)
     assert rc == 0 and fr <= 1e-10
     assert inner[0] / inner[2] < 20   # inner FGMRES(F; AMG) to 1e-2: ~10 V-cycles per application
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The consumer of tools/dump_reference_fixture.cc: what pins the oracle to the real reference the day someone with deal.II +
+# Trilinos runs that program and commits tests/golden/reference_16x6/.  Format: F.txt / Bt.txt / B.txt / Mp.txt = "row col value"
+# per stored entry, residual.txt / delta.txt = "block index value", iterations.txt = outer FGMRES iterations.
+# ---------------------------------------------------------------------------------------------------------------------------
+REFERENCE_FIXTURE = os.path.join(N.ROOT, "tests", "golden", "reference_16x6")
+
+
+def load_reference_fixture(path, n_u, n_p):
+    shapes = {"F": (n_u, n_u), "Bt": (n_u, n_p), "B": (n_p, n_u), "Mp": (n_p, n_p)}
+    out = {}
+    for name, shape in shapes.items():
+        t = np.loadtxt(os.path.join(path, name + ".txt"), ndmin=2)
+        out[name] = sp.csr_matrix((t[:, 2], (t[:, 0].astype(np.int64), t[:, 1].astype(np.int64))), shape=shape)
+    for name in ("residual", "delta"):
+        t = np.loadtxt(os.path.join(path, name + ".txt"), ndmin=2)
+        v = np.zeros(n_u + n_p)
+        v[(t[:, 0].astype(np.int64) * n_u + t[:, 1].astype(np.int64))] = t[:, 2]
+        out[name] = v
+    out["iterations"] = int(open(os.path.join(path, "iterations.txt")).read().split()[0])
+    return out
+
+
+def oracle_state_of_the_fixture():
+    """What the dumper does with the reference's own class: 16 x 6 generated mesh, nu = 1/10, first assembly of the run (Stokes
+    branch, inlet imposed), FGMRES + blockDiagonal to 1e-12."""
+    d = N.Disc.generate(16, 6)
+    o = N.Oracle(d)
+    o.vec(0)[:] = 0; o.vec(2)[:] = 0
+    o.assemble(N.MODE_STOKES, True, 1 / 10.0)
+    blocks = {"F": o.csr(N.BLOCK_F), "Bt": o.csr(N.BLOCK_BT), "B": o.csr(N.BLOCK_B), "Mp": o.csr(N.BLOCK_MP)}
+    residual = o.vec(3).copy()
+    rc, it, _, _ = o.solve(N.STATIONARY, 1, 0, 1e-12, 20000)
+    assert rc == 0
+    return d, blocks, residual, o.vec(2).copy(), it
+
+
+def compare_with_reference_fixture(fix, blocks, residual, delta, its):
+    """Entry by entry where the two DoF numberings coincide (the host stand-in restates deal.II's numbering); otherwise through
+    what no renumbering changes: the sorted stored values of every block, the sorted residual and increment entries."""
+    same_numbering = all((fix[k] != 0).multiply(blocks[k] != 0).nnz == (blocks[k] != 0).nnz for k in blocks)
+    for k, A in blocks.items():
+        R = fix[k]
+        scale = abs(A).max()
+        if same_numbering:
+            assert abs(A - R).max() <= 1e-12 * scale, k
+        else:
+            a, r = np.sort(A.data[A.data != 0]), np.sort(R.data[R.data != 0])
+            assert a.size == r.size and np.abs(a - r).max() <= 1e-12 * scale, k
+    for name, mine, tol in (("residual", residual, 1e-12), ("delta", delta, 1e-8)):
+        ref = fix[name]
+        if same_numbering:
+            assert np.abs(mine - ref).max() <= tol * np.abs(ref).max(), name
+        else:
+            assert np.abs(np.sort(mine) - np.sort(ref)).max() <= tol * np.abs(ref).max(), name
+    assert abs(its - fix["iterations"]) <= max(2, 0.02 * fix["iterations"])
+    return same_numbering
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_FIXTURE), reason="tests/golden/reference_16x6 absent: nobody has run "
+                    "tools/dump_reference_fixture.cc against a deal.II build yet (parity unpinned, DESIGN.md section 2)")
+def test_reference_fixture():
+    d, blocks, residual, delta, its = oracle_state_of_the_fixture()
+    fix = load_reference_fixture(REFERENCE_FIXTURE, d.n_u, d.n_p)
+    compare_with_reference_fixture(fix, blocks, residual, delta, its)
+
+
+def test_reference_fixture_consumer_on_its_own_format(tmp_path):
+    """The consumer above, exercised on files written in the dumper's format from the oracle's own state -- once as they are, once
+    with the dofs renumbered (the numbering-free comparison), once with one perturbed entry (must fail)."""
+    d, blocks, residual, delta, its = oracle_state_of_the_fixture()
+
+    def write(path, blocks_, residual_, delta_):
+        os.makedirs(path, exist_ok=True)
+        for k, A in blocks_.items():
+            C = A.tocoo()
+            np.savetxt(os.path.join(path, k + ".txt"), np.c_[C.row, C.col, C.data], fmt=["%d", "%d", "%.17g"])
+        for name, v in (("residual", residual_), ("delta", delta_)):
+            blk = (np.arange(d.n) >= d.n_u).astype(int)
+            np.savetxt(os.path.join(path, name + ".txt"), np.c_[blk, np.arange(d.n) - blk * d.n_u, v], fmt=["%d", "%d", "%.17g"])
+        open(os.path.join(path, "iterations.txt"), "w").write(f"{its}\n")
+
+    write(tmp_path / "same", blocks, residual, delta)
+    assert compare_with_reference_fixture(load_reference_fixture(tmp_path / "same", d.n_u, d.n_p), blocks, residual, delta, its)
+    rng = np.random.default_rng(5)
+    pu, pp = rng.permutation(d.n_u), rng.permutation(d.n_p)
+    Pu, Pp = sp.eye(d.n_u, format="csr")[pu], sp.eye(d.n_p, format="csr")[pp]
+    moved = {"F": Pu @ blocks["F"] @ Pu.T, "Bt": Pu @ blocks["Bt"] @ Pp.T, "B": Pp @ blocks["B"] @ Pu.T, "Mp": Pp @ blocks["Mp"] @ Pp.T}
+    perm = np.r_[pu, d.n_u + pp]
+    write(tmp_path / "moved", moved, residual[perm], delta[perm])
+    assert not compare_with_reference_fixture(load_reference_fixture(tmp_path / "moved", d.n_u, d.n_p), blocks, residual, delta, its)
+    bad = {k: A.copy() for k, A in blocks.items()}
+    bad["Bt"].data[np.argmax(np.abs(bad["Bt"].data))] *= 1 + 1e-9
+    write(tmp_path / "bad", bad, residual, delta)
+    with pytest.raises(AssertionError):
+        compare_with_reference_fixture(load_reference_fixture(tmp_path / "bad", d.n_u, d.n_p), blocks, residual, delta, its)
